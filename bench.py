@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s per RK stage (FP64) of the explicit FV Euler residual-and-update path
+on a synthetic uniform 3-D isentropic vortex (BASELINE.json metric), on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+
+One "step" = one SSP-RK3 step = 3 RK stages over every cell of the mesh.  value = cells * 3 * K /
+time, the WHOLE-JOB aggregate.  Inputs are resident in HBM when the timed region starts; the state
+arrays (3 x 5 fields x 8 B x cells, 2 GB at 256^3) are far larger than the 126 MB L2, so no extra L2
+flush is needed between timed steps.  `e2e` is the same metric through the C-ABI with HOST buffers:
+upload (pinned AoS) + K steps + download inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/sec per RK stage (FP64)"
+UNIT = "cell-updates/s"
+ALG_BYTES_PER_CELL_STAGE = (80.0, 120.0, 120.0)  # SURVEY 8d / DESIGN.md: stage 1, 2, 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--size", type=int, default=256, help="cells per side per GPU (weak scaling)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-level", type=int, default=0, help="oracle mesh level for the CPU legs (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- synthetic input: isentropic vortex of src/problem.cpp:252-327 at cell centroids ------------
+def vortex_state(dims, offset, global_n, length=10.0, origin=-5.0):
+    """Lexicographic (x fastest) AoS state of the local box; numpy, host side."""
+    h = length / global_n
+    x = origin + (np.arange(dims[0]) + offset[0] + 0.5) * h
+    y = origin + (np.arange(dims[1]) + offset[1] + 0.5) * h
+    X, Y = np.meshgrid(x, y, indexing="xy")            # [ny, nx]
+    r2 = X * X + Y * Y
+    shape = 5.0 / (2 * np.pi) * np.exp(0.5 * (1 - r2))
+    dT = -(1.4 - 1.0) / (2 * 1.4) * shape * shape
+    T = 1.0 + dT
+    p = 1.0 + (np.power(T, 1.4 / (1.4 - 1.0)) - 1.0)
+    u, v = 1.0 - Y * shape, 1.0 + X * shape
+    rho = p / T
+    plane = np.stack([rho, rho * u, rho * v, 0.0 * rho, rho * T / 0.4 + 0.5 * rho * (u * u + v * v)], axis=-1)
+    return plane, h
+
+
+def box_decomposition(n_ranks):
+    """Process grid (px,py,pz) for N = 1,2,4,8 in the order a Morton partition of a cube splits:
+    z first, then y, then x (x is the lowest Morton bit, src/main.cpp:159,183 + PABLO)."""
+    return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[n_ranks]
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.maxes = [], set(), []
+        self.gpu = gpu_index
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.maxes.append(float(out[1]))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(max(self.maxes)),
+                "reasons": sorted(self.reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU legs (the oracle, timed; never on the product path) -------------------------------------
+def cpu_reference_run(level, warmup, steps, threads):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    orc = oracle_lib.load()
+    secs, _ = orc.bench_threads("vortex_xy", 3, level, warmup, steps, threads)
+    cells = (1 << level) ** 3
+    return cells * 3.0 * steps / secs, secs, cells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    level = args.cpu_level or (8 if cores >= 64 else 7)
+    # each "step" of this arm is one RK3 step of the oracle on a (2^level)^3 sample of the workload
+    steps = max(1, min(args.steps, 3))
+    warm = 1  # one untimed step: first-touch page faults of the 5 state/mesh arrays
+    value, secs, cells = cpu_reference_run(level, warm, steps, cores)
+    sample = f"{steps} RK3 steps of vortex_xy on a {1 << level}^3 uniform mesh, {cores} threads (contiguous Morton chunks)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D isentropic vortex (vortex_xy), uniform mesh, order 1, CFL 0.45; CPU sample {1 << level}^3"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference binary cannot be built here (bitpit absent); this is the reference-faithful CPU "
+                "restatement (oracle), which omits bitpit's per-face id lookups and VTK writes",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm --------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+    import minimmerflow_b200 as mmf
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    S = args.size
+    px, py, pz = box_decomposition(world)
+    cz, cy, cx = rank // (px * py), (rank // px) % py, rank % px
+    dims = (S, S, S)
+    gdims = (S * px, S * py, S * pz)
+    offset = (cx * S, cy * S, cz * S)
+    plane, h = vortex_state(dims, offset, gdims[0])
+    cells_local = S ** 3
+    cells_total = cells_local * world
+
+    lib = mmf.load_library()
+    # pinned host AoS buffer (the reference's storage layout), filled plane by plane
+    nbytes = cells_local * 5 * 8
+    hptr = C.c_void_p()
+    mmf._cabi.check(lib.mmf_host_alloc(C.byref(hptr), nbytes))
+    host = np.ctypeslib.as_array((C.c_double * (cells_local * 5)).from_address(hptr.value)).reshape(S, S * S, 5)
+    flat_plane = plane.reshape(-1, 5)
+    for k in range(S):
+        host[k] = flat_plane
+
+    s = mmf.EulerSolver.uniform(dims, h, [mmf.BC_FREE_FLOW] * 6, device=local_rank,
+                                cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC, interface_numbering=mmf.NUMBERING_MORTON,
+                                global_dims=gdims, box_offset=offset)
+    if world > 1:
+        import torch
+        uid = [mmf.EulerSolver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        s.comm_init(rank, world, uid[0])
+        def nb(dx, dy, dz):
+            x, y, z = cx + dx, cy + dy, cz + dz
+            if not (0 <= x < px and 0 <= y < py and 0 <= z < pz):
+                return -1
+            return (z * py + y) * px + x
+        s.comm_set_box_neighbours([nb(-1, 0, 0), nb(1, 0, 0), nb(0, -1, 0), nb(0, 1, 0), nb(0, 0, -1), nb(0, 0, 1)])
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+        s.synchronize()
+
+    cfl, t_inf = 0.45, 1.0e30
+    s.set_state_ptr(mmf.FIELD_U, hptr.value)
+    s.run(cfl, h, 0.0, t_inf, max_steps=max(args.warmup, 3))         # warm-up (>= 3 steps)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = s.info()["kernel_launches"]
+    barrier()
+    s.timer_start()
+    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)                  # exactly K timed steps
+    ms = s.timer_stop()
+    barrier()
+    launches = s.info()["kernel_launches"] - launches0
+    clocks = sampler.stop()
+
+    # per-kernel device time of the fused stage kernels, CUDA events on the launching stream
+    s.profile_begin()
+    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)
+    kms, kn = s.profile_end()
+
+    # e2e: upload + K steps + download through the C-ABI with host buffers, wall clock
+    barrier()
+    t0 = time.perf_counter()
+    s.set_state_ptr(mmf.FIELD_U, hptr.value)
+    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)
+    s.get_state_ptr(mmf.FIELD_U, hptr.value)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        value = cells_total * 3.0 * args.steps / (ms * 1e-3)
+        peak, peak_src = measured_peak()
+        stage_ms = [kms[i] / kn[i] if kn[i] else None for i in (1, 2, 3)]
+        alg = sum(ALG_BYTES_PER_CELL_STAGE) * cells_local
+        achieved = alg / (sum(x for x in stage_ms if x) * 1e-3) / 1e9 if all(stage_ms) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
+                                   f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
+                       "decomposition": f"{px}x{py}x{pz} boxes", "path": "uniform fused stage kernels",
+                       "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "e2e": {"value": cells_total * 3.0 * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": nbytes / args.steps, "d2h_bytes_per_step": nbytes / args.steps,
+                    "what": f"pinned host AoS upload + {args.steps} RK3 steps + download through the C-ABI"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "kernel": "uniform_stage_kernel<1|2|3> (three launches per RK3 step)",
+                         "stage_ms": stage_ms, "algorithmic_bytes_per_cell": list(ALG_BYTES_PER_CELL_STAGE)},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            level = args.cpu_level or 7
+            v, secs, cells = cpu_reference_run(level, 1, 2, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"2 RK3 steps of the same problem on a {1 << level}^3 mesh, {cores} threads, {secs:.1f} s"}
+        print(json.dumps(line), flush=True)
+
+    s.close()
+    lib.mmf_host_free(hptr)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

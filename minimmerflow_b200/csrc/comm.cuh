@@ -1,0 +1,295 @@
+// comm.cuh -- multi-GPU plumbing: one process per GPU, NCCL point-to-point halo exchange over
+// NVLink and a scalar max all-reduce.  Replaces the reference's MPI layer
+// (src/communications.{hpp,tpp,cpp}; call sites src/main.cpp:307-328, 391-395, 425-430, 461-466,
+// 497-502).  NCCL is resolved with dlopen at mmf_comm_init time, so single-GPU use of the library
+// has no NCCL dependency and a process that already loaded torch's NCCL shares that copy.
+#pragma once
+
+#include "mmf_common.cuh"
+#include "uniform_path.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace mmf {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+inline NcclApi &nccl_api() { static NcclApi api; return api; }
+
+static int nccl_load(mmf_ctx *ctx)
+{
+    NcclApi &a = nccl_api();
+    if (a.lib) return MMF_OK;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char *n : names) {
+        a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.lib) break;
+    }
+    if (!a.lib) return fail(ctx, MMF_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define MMF_NCCL_SYM(field, name)                                                                  \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.lib, name));                              \
+    if (!a.field) return fail(ctx, MMF_ERR_NCCL, "libnccl: missing symbol %s", name);
+    MMF_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    MMF_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    MMF_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    MMF_NCCL_SYM(Send, "ncclSend")
+    MMF_NCCL_SYM(Recv, "ncclRecv")
+    MMF_NCCL_SYM(GroupStart, "ncclGroupStart")
+    MMF_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    MMF_NCCL_SYM(AllReduce, "ncclAllReduce")
+    MMF_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef MMF_NCCL_SYM
+    return MMF_OK;
+}
+
+#define MMF_NCCL(ctx, call)                                                                        \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess) {                                                                  \
+            return mmf::fail((ctx), MMF_ERR_NCCL, "%s failed at %s:%d: %s", #call, __FILE__,       \
+                             __LINE__, mmf::nccl_api().GetErrorString(r__));                       \
+        }                                                                                          \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    // generic path ghost lists (GhostCommunicator's exchange lists, src/communications.cpp:621-630)
+    std::vector<int> nbr;
+    std::vector<int64_t> send_off, recv_off; // per neighbour offsets into the id arrays
+    int32_t *d_send_ids = nullptr, *d_recv_ids = nullptr;
+    double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+};
+
+static int comm_unique_id(void *out)
+{
+    if (!out) return fail(nullptr, MMF_ERR_INVALID, "mmf_comm_unique_id: null buffer");
+    int rc = nccl_load(nullptr);
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    MMF_NCCL(nullptr, nccl_api().GetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+    return MMF_OK;
+}
+
+static int comm_init(mmf_ctx *ctx, int rank, int n_ranks, const void *unique_id)
+{
+    if (ctx->comm) return fail(ctx, MMF_ERR_STATE, "mmf_comm_init: communicator already initialised");
+    if (!unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, MMF_ERR_INVALID, "mmf_comm_init: bad arguments");
+    int rc = nccl_load(ctx);
+    if (rc) return rc;
+    Comm *c = new Comm();
+    c->rank = rank;
+    c->n_ranks = n_ranks;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclResult_t r = nccl_api().CommInitRank(&c->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return fail(ctx, MMF_ERR_NCCL, "ncclCommInitRank failed: %s", nccl_api().GetErrorString(r));
+    }
+    ctx->comm = c;
+    return MMF_OK;
+}
+
+static void comm_destroy(mmf_ctx *ctx)
+{
+    if (!ctx->comm) return;
+    if (ctx->comm->comm) nccl_api().CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+}
+
+// MPI_Allreduce(MPI_IN_PLACE, &maxEig, 1, MPI_DOUBLE, MPI_MAX) of src/main.cpp:393, in stream
+int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value)
+{
+    Comm *c = ctx->comm;
+    MMF_NCCL(ctx, nccl_api().AllReduce(d_value, d_value, 1, ncclDouble, ncclMax, c->comm, ctx->stream));
+    return MMF_OK;
+}
+
+// ---- generic path: list-driven pack / unpack ----------------------------------------------------
+// PiercedStorageBufferStreamer<double>::write / read (src/communications.tpp:164-199): for each
+// listed id, nFields consecutive values.
+
+__global__ void __launch_bounds__(256) ghost_pack_kernel(const int32_t *__restrict__ ids, int64_t n, int64_t stride,
+                                                         const double *__restrict__ S, double *__restrict__ buf)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int64_t c = ids[q];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) buf[q * NF + k] = S[k * stride + c];
+}
+
+__global__ void __launch_bounds__(256) ghost_unpack_kernel(const int32_t *__restrict__ ids, int64_t n, int64_t stride,
+                                                           const double *__restrict__ buf, double *__restrict__ S)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int64_t c = ids[q];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) S[k * stride + c] = buf[q * NF + k];
+}
+
+static int comm_set_ghost_lists(mmf_ctx *ctx, int n_nbr, const int32_t *ranks, const int64_t *send_off,
+                                const int64_t *send_ids, const int64_t *recv_off, const int64_t *recv_ids)
+{
+    Comm *c = ctx->comm;
+    if (!c) return fail(ctx, MMF_ERR_STATE, "mmf_comm_set_ghost_lists: call mmf_comm_init first");
+    if (ctx->path != MMF_PATH_GENERIC) return fail(ctx, MMF_ERR_STATE, "ghost lists apply to the generic path");
+    if (n_nbr < 0 || (n_nbr > 0 && (!ranks || !send_off || !send_ids || !recv_off || !recv_ids))) {
+        return fail(ctx, MMF_ERR_INVALID, "mmf_comm_set_ghost_lists: bad arguments");
+    }
+    c->nbr.assign(ranks, ranks + n_nbr);
+    c->send_off.assign(send_off, send_off + n_nbr + 1);
+    c->recv_off.assign(recv_off, recv_off + n_nbr + 1);
+    const int64_t ns = n_nbr ? send_off[n_nbr] : 0, nr = n_nbr ? recv_off[n_nbr] : 0;
+    std::vector<int32_t> s(ns), r(nr);
+    for (int64_t i = 0; i < ns; ++i) {
+        if (send_ids[i] < 0 || send_ids[i] >= ctx->n_cells) return fail(ctx, MMF_ERR_INVALID, "send id out of range");
+        s[i] = (int32_t) send_ids[i];
+    }
+    for (int64_t i = 0; i < nr; ++i) {
+        if (recv_ids[i] < 0 || recv_ids[i] >= ctx->n_cells) return fail(ctx, MMF_ERR_INVALID, "recv id out of range");
+        r[i] = (int32_t) recv_ids[i];
+    }
+    int rc;
+    if ((rc = dev_upload(ctx, &c->d_send_ids, s))) return rc;
+    if ((rc = dev_upload(ctx, &c->d_recv_ids, r))) return rc;
+    if ((rc = dev_alloc(ctx, &c->d_send_buf, (size_t) ns * NF))) return rc;
+    if ((rc = dev_alloc(ctx, &c->d_recv_buf, (size_t) nr * NF))) return rc;
+    return MMF_OK;
+}
+
+static int comm_generic_exchange_enqueue(mmf_ctx *ctx, double *S)
+{
+    Comm *c = ctx->comm;
+    const int n_nbr = (int) c->nbr.size();
+    if (n_nbr == 0) return MMF_OK;
+    const int64_t ns = c->send_off[n_nbr], nr = c->recv_off[n_nbr];
+    if (ns > 0) {
+        ghost_pack_kernel<<<grid_for(ns, 256), 256, 0, ctx->stream>>>(c->d_send_ids, ns, ctx->gm.stride, S, c->d_send_buf);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    MMF_NCCL(ctx, nccl_api().GroupStart());
+    for (int q = 0; q < n_nbr; ++q) {
+        const int64_t s0 = c->send_off[q], s1 = c->send_off[q + 1], r0 = c->recv_off[q], r1 = c->recv_off[q + 1];
+        if (r1 > r0) MMF_NCCL(ctx, nccl_api().Recv(c->d_recv_buf + r0 * NF, (size_t) (r1 - r0) * NF, ncclDouble, c->nbr[q], c->comm, ctx->stream));
+        if (s1 > s0) MMF_NCCL(ctx, nccl_api().Send(c->d_send_buf + s0 * NF, (size_t) (s1 - s0) * NF, ncclDouble, c->nbr[q], c->comm, ctx->stream));
+    }
+    MMF_NCCL(ctx, nccl_api().GroupEnd());
+    if (nr > 0) {
+        ghost_unpack_kernel<<<grid_for(nr, 256), 256, 0, ctx->stream>>>(c->d_recv_ids, nr, ctx->gm.stride, c->d_recv_buf, S);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
+}
+
+// ---- uniform path: face layers of the box -------------------------------------------------------
+
+// layer = -1 / n (ghost) or 0 / n-1 (interior boundary) along `axis`; buf layout [k][b][a]
+__global__ void __launch_bounds__(256) uniform_layer_kernel(const UniformGeom g, double *__restrict__ S,
+                                                            double *__restrict__ buf, int axis, int layer, int to_buf)
+{
+    const int na = (axis == 0) ? g.ny : g.nx;
+    const int nb = (axis == 2) ? g.ny : g.nz;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (a >= na || b >= nb) return;
+    int i, j, k;
+    if (axis == 0)      { i = layer; j = a; k = b; }
+    else if (axis == 1) { i = a; j = layer; k = b; }
+    else                { i = a; j = b; k = layer; }
+    const long long o = uoff(g, i, j, k);
+    const long long per = (long long) na * nb;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        if (to_buf) buf[f * per + (long long) b * na + a] = S[f * g.fs + o];
+        else        S[f * g.fs + o] = buf[f * per + (long long) b * na + a];
+    }
+}
+
+static int comm_set_box_neighbours(mmf_ctx *ctx, const int32_t ranks[6])
+{
+    Comm *c = ctx->comm;
+    if (!c) return fail(ctx, MMF_ERR_STATE, "mmf_comm_set_box_neighbours: call mmf_comm_init first");
+    if (ctx->path != MMF_PATH_UNIFORM) return fail(ctx, MMF_ERR_STATE, "box neighbours apply to the uniform path");
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    for (int s = 0; s < 6; ++s) {
+        const bool partition_side = (g.bc[s] == -2);
+        if (partition_side != (ranks[s] >= 0)) {
+            return fail(ctx, MMF_ERR_INVALID, "side %d: neighbour rank given iff the side is a partition boundary", s);
+        }
+        if (ranks[s] >= c->n_ranks) return fail(ctx, MMF_ERR_INVALID, "side %d: neighbour rank out of range", s);
+        u->nbr_rank[s] = ranks[s];
+        if (ranks[s] >= 0 && !u->send_buf[s]) {
+            const int axis = s >> 1;
+            const size_t n = (size_t) NF * ((axis == 0) ? g.ny : g.nx) * ((axis == 2) ? g.ny : g.nz);
+            int rc;
+            if ((rc = dev_alloc(ctx, &u->send_buf[s], n))) return rc;
+            if ((rc = dev_alloc(ctx, &u->recv_buf[s], n))) return rc;
+        }
+    }
+    return MMF_OK;
+}
+
+int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S)
+{
+    Comm *c = ctx->comm;
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    bool any = false;
+    for (int s = 0; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        any = true;
+        const int axis = s >> 1;
+        const int n_ax = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
+        const int na = (axis == 0) ? g.ny : g.nx, nb = (axis == 2) ? g.ny : g.nz;
+        dim3 grid((na + 255) / 256, nb);
+        uniform_layer_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, u->send_buf[s], axis, (s & 1) ? n_ax - 1 : 0, 1);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    if (!any) return MMF_OK;
+    MMF_NCCL(ctx, nccl_api().GroupStart());
+    for (int s = 0; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        const int axis = s >> 1;
+        const size_t n = (size_t) NF * ((axis == 0) ? g.ny : g.nx) * ((axis == 2) ? g.ny : g.nz);
+        MMF_NCCL(ctx, nccl_api().Recv(u->recv_buf[s], n, ncclDouble, u->nbr_rank[s], c->comm, ctx->stream));
+        MMF_NCCL(ctx, nccl_api().Send(u->send_buf[s], n, ncclDouble, u->nbr_rank[s], c->comm, ctx->stream));
+    }
+    MMF_NCCL(ctx, nccl_api().GroupEnd());
+    for (int s = 0; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        const int axis = s >> 1;
+        const int n_ax = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
+        const int na = (axis == 0) ? g.ny : g.nx, nb = (axis == 2) ? g.ny : g.nz;
+        dim3 grid((na + 255) / 256, nb);
+        uniform_layer_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, u->recv_buf[s], axis, (s & 1) ? n_ax : -1, 0);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
+}
+
+static int comm_exchange_enqueue(mmf_ctx *ctx, int field)
+{
+    if (ctx->path == MMF_PATH_UNIFORM) return comm_uniform_exchange_enqueue(ctx, uniform_field_ptr(ctx, field));
+    return comm_generic_exchange_enqueue(ctx, ctx->fields[field]);
+}
+
+} // namespace mmf

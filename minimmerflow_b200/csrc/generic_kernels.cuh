@@ -1,0 +1,202 @@
+// generic_kernels.cuh -- connectivity-driven kernels that work on ANY mesh the host describes
+// (non-uniform octree levels, bodies / BC_WALL, BC_DIRICHLET, 2-D).
+//
+// Residual assembly is a CELL GATHER: one thread owns one cell and walks that cell's interfaces in
+// the host's interface processing order, applying `-=` on the owner side and `+=` on the neighbour
+// side.  That is the order in which the reference's scatter loop (src/euler.cpp:153-248) touches
+// the cell, so the RHS is reproduced bit for bit without atomics.
+#pragma once
+
+#include "gas.cuh"
+
+#include <stdint.h>
+
+namespace mmf {
+
+struct GenericMesh {
+    int64_t n_cells;
+    int64_t n_ifaces;
+    int64_t stride;           // SoA field stride (>= n_cells)
+    // cell -> ordered interface entries, entry = (interface raw id << 1) | side (0 owner, 1 neigh);
+    // only processed interfaces of solved cells are listed
+    const int64_t *cf_ptr;    // [n_cells + 1]
+    const int32_t *cf_ent;
+    // per interface, raw id indexed
+    const int32_t *f_owner;
+    const int32_t *f_neigh;   // -1 border
+    const int8_t  *f_bc;
+    const double  *f_area;
+    const double  *f_normal;  // SoA [e * n_ifaces + f]
+    // per cell
+    const uint8_t *c_solved;
+    const uint8_t *c_update;  // internal AND solved
+    const double  *c_volume;
+    double dirichlet_info[NF];
+};
+
+// ---- host AoS (raw order, [c*5+k]) <-> device SoA ([k*stride+c]) -------------------------------
+
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa,
+                                                         int64_t n_cells, int64_t stride)
+{
+    // coalesced read of the AoS stream through shared memory, coalesced write per field
+    __shared__ double tile[256 * NF];
+    const int64_t c0 = (int64_t) blockIdx.x * 256;
+    const int64_t n  = min((int64_t) 256, n_cells - c0);
+    for (int i = threadIdx.x; i < n * NF; i += 256) tile[i] = aos[c0 * NF + i];
+    __syncthreads();
+    if (threadIdx.x < n) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) soa[k * stride + c0 + threadIdx.x] = tile[threadIdx.x * NF + k];
+    }
+}
+
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(const double *__restrict__ soa, double *__restrict__ aos,
+                                                         int64_t n_cells, int64_t stride)
+{
+    __shared__ double tile[256 * NF];
+    const int64_t c0 = (int64_t) blockIdx.x * 256;
+    const int64_t n  = min((int64_t) 256, n_cells - c0);
+    if (threadIdx.x < n) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) tile[threadIdx.x * NF + k] = soa[k * stride + c0 + threadIdx.x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * NF; i += 256) aos[c0 * NF + i] = tile[i];
+}
+
+// ---- euler::computeRHS (src/euler.cpp:127-249) --------------------------------------------------
+
+__device__ __forceinline__ void load_cell(const double *__restrict__ S, int64_t stride, int64_t c, double *u)
+{
+#pragma unroll
+    for (int k = 0; k < NF; ++k) u[k] = S[k * stride + c];
+}
+
+__global__ void __launch_bounds__(128) generic_rhs_kernel(GenericMesh m, const double *__restrict__ S,
+                                                          double *__restrict__ RHS, double *__restrict__ max_eig)
+{
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double lmax = 0.0;
+    if (c < m.n_cells) {
+        // RHS starts at zero for every cell, solved or not (src/euler.cpp:135-148)
+        double acc[NF] = { 0., 0., 0., 0., 0. };
+        const int64_t e0 = m.cf_ptr[c], e1 = m.cf_ptr[c + 1];
+        for (int64_t e = e0; e < e1; ++e) {
+            const int32_t ent  = m.cf_ent[e];
+            const int32_t f    = ent >> 1;
+            const int     side = ent & 1;
+            const int32_t o    = m.f_owner[f];
+            const int32_t nb   = m.f_neigh[f];
+            const int     bc   = m.f_bc[f];
+            const double  A    = m.f_area[f];
+            const double  nrm[3] = { m.f_normal[f], m.f_normal[m.n_ifaces + f], m.f_normal[2 * m.n_ifaces + f] };
+
+            double ownerRec[NF], neighRec[NF];
+            if (bc == BC_NONE) {
+                // order-1 reconstruction: face state = cell mean (src/reconstruction.cpp:90-97)
+                load_cell(S, m.stride, o, ownerRec);
+                load_cell(S, m.stride, nb, neighRec);
+            } else {
+                // src/euler.cpp:198-225: the fluid side is the owner when it is solved, otherwise
+                // the neighbour; the flipped normal is used for the BC evaluation only
+                const bool ownerSolved = m.c_solved[o] != 0;
+                if (ownerSolved) {
+                    load_cell(S, m.stride, o, ownerRec);
+                    interface_bc_values(bc, nrm, m.dirichlet_info, ownerRec, neighRec);
+                } else {
+                    const double flipped[3] = { -1. * nrm[0], -1. * nrm[1], -1. * nrm[2] };
+                    load_cell(S, m.stride, nb, neighRec);
+                    interface_bc_values(bc, flipped, m.dirichlet_info, neighRec, ownerRec);
+                }
+            }
+
+            double flux[NF], lambda;
+            eval_splitting(ownerRec, neighRec, nrm, flux, &lambda); // un-flipped normal (:232)
+            lmax = (lambda < lmax) ? lmax : lambda;                  // :234
+
+            if (side == 0) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) acc[k] -= A * flux[k];  // :237-241
+            } else {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) acc[k] += A * flux[k];  // :243-247
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NF; ++k) RHS[k * m.stride + c] = acc[k];
+    }
+    block_max_to_global(lmax, max_eig);
+}
+
+// ---- time-step control block, device resident --------------------------------------------------
+// Lets a whole RK3 step (and a batch of steps) be enqueued without any host round trip:
+// dt is chosen on the device from the stage-1 max eigenvalue exactly like src/main.cpp:398-402,
+// and steps enqueued past t_max switch themselves off through `active`.
+struct StepControl {
+    double t, dt, t_max, cfl, min_h, steps, active;
+    double max_eig[3];   // per-stage max face eigenvalue (src/main.cpp:399, :440, :476)
+    double max_eig_chk;  // uniform path: stage-1 face maximum re-derived by the fused kernel
+};
+
+// ---- RK stage loops (src/main.cpp:409-423, 445-459, 481-495) -----------------------------------
+
+template <int STAGE>
+__global__ void __launch_bounds__(256) generic_rk_kernel(int64_t n_cells, int64_t stride,
+                                                         const uint8_t *__restrict__ update,
+                                                         const double *__restrict__ volume,
+                                                         const StepControl *__restrict__ ctl,
+                                                         double *__restrict__ U, double *__restrict__ W,
+                                                         const double *__restrict__ RHS)
+{
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctl->active == 0.0) return;
+    if (c >= n_cells || !update[c]) return;
+    const double dt = ctl->dt;
+    const double V  = volume[c];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+        const int64_t i = k * stride + c;
+        const double  q = dt * RHS[i] / V;
+        if (STAGE == 1) {
+            W[i] = U[i] + q;
+        } else if (STAGE == 2) {
+            W[i] = 0.75 * U[i] + 0.25 * (W[i] + q);
+        } else {
+            U[i] = (1. / 3) * U[i] + (2. / 3) * (W[i] + q);
+        }
+    }
+}
+
+// Runs after the stage-1 residual: `while (t < tMax)` test (src/main.cpp:377) and the dt choice
+// dt = 0.9*cfl*minCellSize/maxEig; if (t+dt > tMax) dt = tMax-t  (src/main.cpp:398-402).
+__global__ void choose_dt_kernel(StepControl *ctl)
+{
+    if (ctl->t < ctl->t_max) {
+        double dt = 0.9 * ctl->cfl * ctl->min_h / ctl->max_eig[0];
+        if (ctl->t + dt > ctl->t_max) dt = ctl->t_max - ctl->t;
+        ctl->dt     = dt;
+        ctl->active = 1.0;
+    } else {
+        ctl->dt     = 0.0;
+        ctl->active = 0.0;
+    }
+}
+
+// host-chosen dt (mmf_rk_stage keeps main.cpp's own dt logic on the host)
+__global__ void set_dt_kernel(StepControl *ctl, double dt)
+{
+    ctl->dt     = dt;
+    ctl->active = 1.0;
+}
+
+// src/main.cpp:505-506
+__global__ void advance_time_kernel(StepControl *ctl)
+{
+    if (ctl->active != 0.0) {
+        ctl->t += ctl->dt;
+        ctl->steps += 1.0;
+    }
+}
+
+} // namespace mmf

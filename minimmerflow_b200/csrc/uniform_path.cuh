@@ -1,0 +1,438 @@
+// uniform_path.cuh -- host side of MMF_PATH_UNIFORM: eligibility check of a host mesh description,
+// padded SoA allocation, launch configuration and the per-step kernel sequence.
+#pragma once
+
+#include "mmf_common.cuh"
+#include "uniform_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace mmf {
+
+struct UniformPath {
+    UniformGeom g{};
+    int cell_numbering = NUM_MORTON;  // raw id <-> lattice (ignored when cell_off is set)
+    int iface_numbering = NUM_MORTON; // accumulation order
+    int order_exact = 1;
+    int *cell_off = nullptr;          // optional explicit raw id -> padded offset
+    double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
+    int w_cur = 1;                    // which array currently holds field W
+    int nw = 16;                      // warps per CTA of the stage kernel
+    int lz = 0;                       // planes per CTA
+    bool eig_valid = false;
+    int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
+    double *send_buf[6] = {}, *recv_buf[6] = {};
+};
+
+inline int uniform_order_exact(const mmf_ctx *ctx) { return ctx->uni ? ctx->uni->order_exact : 0; }
+inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_valid = false; }
+
+inline void uniform_destroy(mmf_ctx *ctx)
+{
+    delete ctx->uni;
+    ctx->uni = nullptr;
+}
+
+static inline double *uniform_field_ptr(mmf_ctx *ctx, int field)
+{
+    UniformPath *u = ctx->uni;
+    if (field == MMF_FIELD_U) return u->arr[0];
+    if (field == MMF_FIELD_W) return u->arr[u->w_cur];
+    return u->arr[3];
+}
+
+static int uniform_ensure_rhs(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    if (u->arr[3]) return MMF_OK;
+    int rc = dev_alloc(ctx, &u->arr[3], (size_t) NF * u->g.fs);
+    if (rc) return rc;
+    MMF_CUDA(ctx, cudaMemsetAsync(u->arr[3], 0, sizeof(double) * NF * u->g.fs, ctx->stream));
+    return MMF_OK;
+}
+
+// ---- launch helpers -----------------------------------------------------------------------------
+
+template <int STAGE, int ORDER, int NW>
+static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    auto kern = uniform_stage_kernel<STAGE, ORDER, NW>;
+    const size_t smem = (size_t) NW * 16 * 32 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (NW - 2) - 1) / (NW - 2), (g.nz + u->lz - 1) / u->lz);
+    {
+        ScopedLaunchTimer timer(ctx, STAGE);
+        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
+template <int STAGE, int ORDER>
+static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
+{
+    if (ctx->uni->nw == 8) return launch_stage_t<STAGE, ORDER, 8>(ctx, Sin, Un, Out, d_max);
+    return launch_stage_t<STAGE, ORDER, 16>(ctx, Sin, Un, Out, d_max);
+}
+
+template <int STAGE>
+static int launch_stage(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
+{
+    switch (ctx->uni->iface_numbering) {
+    case NUM_MORTON: return launch_stage_o<STAGE, NUM_MORTON>(ctx, Sin, Un, Out, d_max);
+    case NUM_LEXI:   return launch_stage_o<STAGE, NUM_LEXI>(ctx, Sin, Un, Out, d_max);
+    default:         return launch_stage_o<STAGE, NUM_AXIS>(ctx, Sin, Un, Out, d_max);
+    }
+}
+
+int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S); // comm.cuh
+
+// refresh the ghost shell of a padded array: physical sides from the BC, partition sides by exchange
+static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active)
+{
+    const UniformGeom &g = ctx->uni->g;
+    const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
+    dim3 grid((na + 255) / 256, nb, 6);
+    uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active);
+    MMF_LAUNCH_CHECK(ctx);
+    if (ctx->comm) return comm_uniform_exchange_enqueue(ctx, S);
+    return MMF_OK;
+}
+
+// ---- creation -----------------------------------------------------------------------------------
+
+static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
+{
+    UniformGeom &g = u->g;
+    g.px = (g.nx + 2 + 3) / 4 * 4;
+    g.py = g.ny + 2;
+    g.pz = g.nz + 2;
+    g.fs = ((long long) g.px * g.py * g.pz + 15) / 16 * 16;
+    if (g.fs * NF >= ((long long) 1 << 31) * 4) return fail(ctx, MMF_ERR_INVALID, "uniform box too large");
+    int rc;
+    for (int a = 0; a < 3; ++a) {
+        if ((rc = dev_alloc(ctx, &u->arr[a], (size_t) NF * g.fs))) return rc;
+        fill_benign_kernel<<<grid_for(g.fs, 256), 256, 0, ctx->stream>>>(u->arr[a], g.fs);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    // launch shape: 16-warp CTAs when the box is tall enough in y, z chunks sized so that the grid
+    // covers the SMs several times over
+    const char *env_nw = getenv("MMF_STAGE_WARPS");
+    u->nw = env_nw ? atoi(env_nw) : 16;
+    if (u->nw != 8 && u->nw != 16) u->nw = 16;
+    const char *env_lz = getenv("MMF_STAGE_LZ");
+    if (env_lz && atoi(env_lz) > 0) {
+        u->lz = atoi(env_lz);
+    } else {
+        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + u->nw - 3) / (u->nw - 2));
+        const long long sms = ctx->prop.multiProcessorCount;
+        const long long ctas_per_sm = (u->nw == 8) ? 2 : 1;
+        // aim for >= 4 waves, but keep chunks long enough (>= 16 planes) to amortise the prologue
+        long long chunks = (4 * sms * ctas_per_sm + tiles_xy - 1) / tiles_xy;
+        chunks = std::max<long long>(1, std::min<long long>(chunks, std::max(1, g.nz / 16)));
+        u->lz = (int) ((g.nz + chunks - 1) / chunks);
+    }
+    MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMF_OK;
+}
+
+static int uniform_create(mmf_ctx *ctx, const mmf_uniform_desc *d)
+{
+    for (int e = 0; e < 3; ++e) {
+        if (d->box_dims[e] <= 0 || d->global_dims[e] < d->box_dims[e] || d->box_offset[e] < 0 ||
+            d->box_offset[e] + d->box_dims[e] > d->global_dims[e]) {
+            return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: inconsistent box along axis %d", e);
+        }
+    }
+    if (!(d->h > 0.)) return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: h must be positive");
+    if (d->cell_numbering != MMF_NUMBERING_MORTON && d->cell_numbering != MMF_NUMBERING_LEXICOGRAPHIC) {
+        return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: cell_numbering must be MORTON or LEXICOGRAPHIC");
+    }
+    if (d->interface_numbering < 0 || d->interface_numbering > 2) {
+        return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: unknown interface_numbering");
+    }
+    if (d->cell_numbering == MMF_NUMBERING_MORTON) {
+        const int n = d->box_dims[0];
+        if (n != d->box_dims[1] || n != d->box_dims[2] || (n & (n - 1))) {
+            return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: Morton cell numbering needs a power-of-two cube");
+        }
+    }
+    UniformPath *u = new UniformPath();
+    ctx->uni = u;
+    UniformGeom &g = u->g;
+    g.nx = d->box_dims[0]; g.ny = d->box_dims[1]; g.nz = d->box_dims[2];
+    g.gx0 = d->box_offset[0]; g.gy0 = d->box_offset[1]; g.gz0 = d->box_offset[2];
+    g.gnx = d->global_dims[0]; g.gny = d->global_dims[1]; g.gnz = d->global_dims[2];
+    g.h = d->h;
+    g.area = g.h * g.h;
+    g.volume = g.h * g.h * g.h;
+    for (int s = 0; s < 6; ++s) {
+        const int axis = s >> 1;
+        const bool hi = s & 1;
+        const bool at_border = hi ? (d->box_offset[axis] + d->box_dims[axis] == d->global_dims[axis])
+                                  : (d->box_offset[axis] == 0);
+        if (at_border) {
+            if (d->bc_side[s] < MMF_BC_FREE_FLOW || d->bc_side[s] > MMF_BC_DIRICHLET) {
+                return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: side %d needs a boundary condition", s);
+            }
+            g.bc[s] = d->bc_side[s];
+        } else {
+            g.bc[s] = -2;
+        }
+    }
+    memcpy(g.dirichlet, d->dirichlet_info, sizeof g.dirichlet);
+    u->cell_numbering = d->cell_numbering;
+    u->iface_numbering = d->interface_numbering;
+    u->order_exact = (d->interface_numbering != MMF_NUMBERING_AXIS) && !(d->flags & MMF_FLAG_ORDER_AXIS);
+    if (d->flags & MMF_FLAG_ORDER_AXIS) u->iface_numbering = NUM_AXIS;
+    ctx->path = MMF_PATH_UNIFORM;
+    ctx->n_cells = (int64_t) g.nx * g.ny * g.nz;
+    ctx->n_ifaces = (int64_t) (g.nx + 1) * g.ny * g.nz + (int64_t) g.nx * (g.ny + 1) * g.nz + (int64_t) g.nx * g.ny * (g.nz + 1);
+    return uniform_alloc(ctx, u);
+}
+
+// Per-cell order in which the reference's interface loop touches the six faces, predicted from a
+// numbering convention; slots: 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z.
+static void predicted_face_order(int numbering, const int ijk[3], int order[6])
+{
+    int n = 0;
+    int lows[3], keys[3], nl = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (ijk[a] == 0) continue;
+        lows[nl] = a;
+        if (numbering == NUM_MORTON) keys[nl] = 3 * __builtin_ctz((unsigned) ijk[a]) + a;
+        else                         keys[nl] = a == 2 ? 2 : a == 1 ? 1 : 0; // lexicographic: z, y, x
+        nl++;
+    }
+    // descending key first
+    for (int a = 0; a < nl; ++a)
+        for (int b = a + 1; b < nl; ++b)
+            if (keys[b] > keys[a]) { std::swap(keys[a], keys[b]); std::swap(lows[a], lows[b]); }
+    for (int a = 0; a < nl; ++a) order[n++] = 2 * lows[a];
+    for (int a = 0; a < 3; ++a) {
+        if (ijk[a] == 0) order[n++] = 2 * a;
+        order[n++] = 2 * a + 1;
+    }
+}
+
+// Decide whether a host mesh description is a full, conforming, uniform, all-solved 3-D box whose
+// interface numbering matches a known convention; if so build the uniform path from it.
+static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
+{
+    *used = false;
+    if (!d->cell_ijk || d->dim != 3 || (d->flags & MMF_FLAG_FORCE_GENERIC)) return MMF_OK;
+    const int nx = d->box_dims[0], ny = d->box_dims[1], nz = d->box_dims[2];
+    if (nx <= 0 || ny <= 0 || nz <= 0) return MMF_OK;
+    const int64_t nc = d->n_cells, nf = d->n_interfaces;
+    if ((int64_t) nx * ny * nz != nc) return MMF_OK;
+    for (int e = 0; e < 3; ++e) {
+        if (d->global_dims[e] != d->box_dims[e] || d->box_offset[e] != 0) return MMF_OK; // single-box only
+    }
+    const int64_t nf_expected = (int64_t) (nx + 1) * ny * nz + (int64_t) nx * (ny + 1) * nz + (int64_t) nx * ny * (nz + 1);
+    if (nf != nf_expected) return MMF_OK;
+    if (d->interface_order && d->n_interfaces_listed != nf) return MMF_OK;
+
+    // cells: a bijection onto the lattice, all solved and internal, one volume
+    std::vector<int64_t> lattice_to_raw((size_t) nc, -1);
+    const double V = d->volume[0];
+    for (int64_t c = 0; c < nc; ++c) {
+        const int i = d->cell_ijk[3 * c], j = d->cell_ijk[3 * c + 1], k = d->cell_ijk[3 * c + 2];
+        if (i < 0 || i >= nx || j < 0 || j >= ny || k < 0 || k >= nz) return MMF_OK;
+        const int64_t l = ((int64_t) k * ny + j) * nx + i;
+        if (lattice_to_raw[l] >= 0) return MMF_OK;
+        lattice_to_raw[l] = c;
+        if (!d->solved[c] || (d->internal && !d->internal[c]) || d->volume[c] != V) return MMF_OK;
+    }
+    const double A = d->area[0];
+    const double h = std::sqrt(A);
+
+    // interfaces: axis-aligned unit normals owner->neigh between lattice neighbours, one area,
+    // one BC per side; record for every cell the position of each of its six faces
+    std::vector<int64_t> face_pos((size_t) nc * 6, -1);
+    int bc_side[6] = { -9, -9, -9, -9, -9, -9 };
+    for (int64_t q = 0; q < nf; ++q) {
+        const int64_t f = d->interface_order ? d->interface_order[q] : q;
+        if (f < 0 || f >= nf) return MMF_OK;
+        const int64_t o = d->owner[f], n = d->neigh[f];
+        if (o < 0 || o >= nc || n >= nc || d->area[f] != A) return MMF_OK;
+        int axis = -1, sgn = 0;
+        for (int e = 0; e < 3; ++e) {
+            const double v = d->normal[3 * f + e];
+            if (v == 1.0 || v == -1.0) { if (axis >= 0) return MMF_OK; axis = e; sgn = (int) v; }
+            else if (v != 0.0) return MMF_OK;
+        }
+        if (axis < 0) return MMF_OK;
+        const int *oc = &d->cell_ijk[3 * o];
+        if (n >= 0) {
+            const int *ncell = &d->cell_ijk[3 * n];
+            for (int e = 0; e < 3; ++e) {
+                if (ncell[e] - oc[e] != (e == axis ? sgn : 0)) return MMF_OK;
+            }
+            if (d->bc[f] != MMF_BC_NONE) return MMF_OK;
+            const int so = 2 * axis + (sgn > 0 ? 1 : 0), sn = 2 * axis + (sgn > 0 ? 0 : 1);
+            if (face_pos[o * 6 + so] >= 0 || face_pos[n * 6 + sn] >= 0) return MMF_OK;
+            face_pos[o * 6 + so] = q;
+            face_pos[n * 6 + sn] = q;
+        } else {
+            const int side = 2 * axis + (sgn > 0 ? 1 : 0);
+            const int lim = (axis == 0 ? nx : axis == 1 ? ny : nz) - 1;
+            if (oc[axis] != (sgn > 0 ? lim : 0)) return MMF_OK; // outward normal on the matching side
+            if (d->bc[f] < MMF_BC_FREE_FLOW || d->bc[f] > MMF_BC_DIRICHLET) return MMF_OK;
+            if (bc_side[side] == -9) bc_side[side] = d->bc[f];
+            else if (bc_side[side] != d->bc[f]) return MMF_OK;
+            if (face_pos[o * 6 + side] >= 0) return MMF_OK;
+            face_pos[o * 6 + side] = q;
+        }
+    }
+    for (size_t x = 0; x < face_pos.size(); ++x) if (face_pos[x] < 0) return MMF_OK;
+
+    // which numbering convention reproduces the host's per-cell interface order?
+    int numbering = -1;
+    for (int cand = 0; cand < 2 && numbering < 0; ++cand) {
+        bool ok = true;
+        for (int64_t c = 0; c < nc && ok; ++c) {
+            int order[6];
+            predicted_face_order(cand, &d->cell_ijk[3 * c], order);
+            for (int s = 0; s + 1 < 6; ++s) {
+                if (face_pos[c * 6 + order[s]] >= face_pos[c * 6 + order[s + 1]]) { ok = false; break; }
+            }
+        }
+        if (ok) numbering = cand;
+    }
+    int order_exact = 1;
+    if (numbering < 0) {
+        if (!(d->flags & MMF_FLAG_ORDER_AXIS)) return MMF_OK; // unknown order: stay on the exact generic path
+        numbering = NUM_AXIS;
+        order_exact = 0;
+    }
+    if (d->flags & MMF_FLAG_ORDER_AXIS) { numbering = NUM_AXIS; order_exact = 0; }
+
+    UniformPath *u = new UniformPath();
+    ctx->uni = u;
+    UniformGeom &g = u->g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.gx0 = g.gy0 = g.gz0 = 0;
+    g.gnx = nx; g.gny = ny; g.gnz = nz;
+    g.h = h;
+    g.area = A;   // taken verbatim from the host tables, never rebuilt from h
+    g.volume = V;
+    for (int s = 0; s < 6; ++s) g.bc[s] = bc_side[s];
+    memcpy(g.dirichlet, d->dirichlet_info, sizeof g.dirichlet);
+    u->iface_numbering = numbering;
+    u->order_exact = order_exact;
+    ctx->path = MMF_PATH_UNIFORM;
+    int rc = uniform_alloc(ctx, u);
+    if (rc) return rc;
+    std::vector<int> off((size_t) nc);
+    for (int64_t c = 0; c < nc; ++c) {
+        off[c] = (int) uoff(g, d->cell_ijk[3 * c], d->cell_ijk[3 * c + 1], d->cell_ijk[3 * c + 2]);
+    }
+    if ((rc = dev_upload(ctx, &u->cell_off, off))) return rc;
+    *used = true;
+    return MMF_OK;
+}
+
+// ---- state transfer -----------------------------------------------------------------------------
+
+static int uniform_scatter_state(mmf_ctx *ctx, int field, const double *staging)
+{
+    UniformPath *u = ctx->uni;
+    int rc;
+    if (field == MMF_FIELD_RHS && (rc = uniform_ensure_rhs(ctx))) return rc;
+    double *S = uniform_field_ptr(ctx, field);
+    uniform_scatter_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
+        u->g, u->cell_numbering, u->cell_off, staging, S, ctx->n_cells);
+    MMF_LAUNCH_CHECK(ctx);
+    if (field == MMF_FIELD_U) u->eig_valid = false;
+    if (field != MMF_FIELD_RHS) return uniform_refresh_ghosts(ctx, S, 0);
+    return MMF_OK;
+}
+
+static int uniform_gather_state(mmf_ctx *ctx, int field, double *staging)
+{
+    UniformPath *u = ctx->uni;
+    int rc;
+    if (field == MMF_FIELD_RHS && (rc = uniform_ensure_rhs(ctx))) return rc;
+    const double *S = uniform_field_ptr(ctx, field);
+    uniform_gather_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
+        u->g, u->cell_numbering, u->cell_off, S, staging, ctx->n_cells);
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
+// ---- operators ----------------------------------------------------------------------------------
+
+// euler::computeRHS on the uniform path: the stage kernel with STAGE 0 (RHS materialised)
+static int uniform_rhs(mmf_ctx *ctx, int field, double *d_max)
+{
+    int rc = uniform_ensure_rhs(ctx);
+    if (rc) return rc;
+    const double *S = uniform_field_ptr(ctx, field);
+    return launch_stage<0>(ctx, S, S, ctx->uni->arr[3], d_max);
+}
+
+static int uniform_rk(mmf_ctx *ctx, int stage)
+{
+    UniformPath *u = ctx->uni;
+    int rc = uniform_ensure_rhs(ctx);
+    if (rc) return rc;
+    const UniformGeom &g = u->g;
+    dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
+    double *U = u->arr[0], *W = u->arr[u->w_cur], *R = u->arr[3];
+    switch (stage) {
+    case 1: uniform_rk_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
+    case 2: uniform_rk_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
+    default: uniform_rk_kernel<3><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    if (stage == 3) u->eig_valid = false;
+    return uniform_refresh_ghosts(ctx, stage == 3 ? U : W, 0);
+}
+
+int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value); // comm.cuh
+
+// One fused SSP-RK3 step (replaces src/main.cpp:383-506):
+//   max eigenvalue of U -> dt on the device -> three fused residual+update kernels, each followed
+//   by the ghost refresh of its output.
+static int uniform_step(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    StepControl *c = ctx->d_ctl;
+    int rc;
+    double *U = u->arr[0], *Wa = u->arr[1], *Wb = u->arr[2];
+
+    MMF_CUDA(ctx, cudaMemsetAsync(&c->max_eig[0], 0, 4 * sizeof(double), ctx->stream));
+    {
+        dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2);
+        uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0]))) return rc;
+    choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
+    MMF_LAUNCH_CHECK(ctx);
+
+    // the stage-1 kernel re-derives the same face maximum as a by-product; it is kept beside the
+    // value that chose dt and mmf_step fails loudly if the two evaluations ever disagree
+    if ((rc = launch_stage<1>(ctx, U, U, Wa, &c->max_eig_chk))) return rc;
+    if ((rc = uniform_refresh_ghosts(ctx, Wa, 1))) return rc;
+    if ((rc = launch_stage<2>(ctx, Wa, U, Wb, &c->max_eig[1]))) return rc;
+    if ((rc = uniform_refresh_ghosts(ctx, Wb, 1))) return rc;
+    if ((rc = launch_stage<3>(ctx, Wb, U, U, &c->max_eig[2]))) return rc;
+    if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
+    u->w_cur = 2;
+    advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c);
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
+} // namespace mmf

@@ -1,0 +1,214 @@
+"""GPU parity, uniform fused path (the benchmark path), through the C-ABI.
+
+The fused kernels compute every interface once, share per-cell primitives, divide with a shared
+reciprocal and accumulate in the host's interface-id order: the results must still be BITWISE equal
+to the reference-shaped oracle, not just within north_star's 1e-12 relative."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_3D = [c for c in golden_cases() if c["dim"] == 3]
+
+
+def test_shared_reciprocal_division_is_ieee(mmf):
+    assert mmf.selftest_division(n_samples=1 << 30, seed=2024) == 0
+
+
+def _bc_sides(m):
+    border = m["neigh"] < 0
+    code = int(m["bc"][border][0])
+    assert np.all(m["bc"][border] == code)
+    return [code] * 6
+
+
+@pytest.mark.parametrize("problem,n", [("vortex_xy", 32), ("vortex_yz", 16), ("radsod", 32), ("sod3d_z", 8)])
+def test_uniform_path_selected_and_rhs_bit_exact(mmf, oracle, problem, n):
+    m = oracle.problem_mesh(problem, 3, n)
+    U = oracle.init_state(m)
+    ref, ref_eig = oracle.compute_rhs(m, U)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        info = s.info()
+        assert info["path"] == mmf.PATH_UNIFORM and info["order_exact"] == 1
+        s.set_state(mmf.FIELD_U, U)
+        assert bits_equal(s.get_state(mmf.FIELD_U), U)
+        eig = s.compute_rhs(mmf.FIELD_U)
+        got = s.get_state(mmf.FIELD_RHS)
+    assert eig == ref_eig
+    assert bits_equal(got, ref)
+
+
+def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
+    """Random (non-smooth) states exercise every rounding path; all three side BC kinds."""
+    rng = np.random.default_rng(7)
+    for problem in ("radsod", "vortex_xy"):
+        m = oracle.problem_mesh(problem, 3, 16)
+        nc = m["volume"].shape[0]
+        rho = rng.uniform(0.3, 2.0, nc); vel = rng.uniform(-2, 2, (nc, 3)); p = rng.uniform(0.2, 3, nc)
+        U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+        ref, ref_eig = oracle.compute_rhs(m, U)
+        with mmf.EulerSolver.from_mesh(m) as s:
+            s.set_state(mmf.FIELD_U, U)
+            eig = s.compute_rhs(mmf.FIELD_U)
+            got = s.get_state(mmf.FIELD_RHS)
+        assert eig == ref_eig and bits_equal(got, ref), problem
+
+
+@pytest.mark.parametrize("warps", ["8", "16"])
+def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, warps):
+    monkeypatch.setenv("MMF_STAGE_WARPS", warps)
+    monkeypatch.setenv("MMF_STAGE_LZ", "5")          # ragged z chunks on purpose
+    m = oracle.problem_mesh("vortex_xy", 3, 32)
+    U = oracle.init_state(m)
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+        s.set_state(mmf.FIELD_U, U)
+        t = 0.0
+        for _ in range(10):
+            dto, me3 = oracle.step(m, 0.45, t, 2.0, Uo, Wo, Ro)
+            dtg, meg = s.step(0.45, m["h"], t, 2.0)
+            assert dtg == dto and list(me3) == meg
+            t += dto
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+        assert bits_equal(s.get_state(mmf.FIELD_W), Wo)
+
+
+def test_unfused_operator_sequence_on_uniform_path(mmf, oracle):
+    m = oracle.problem_mesh("radsod", 3, 16)
+    U = oracle.init_state(m)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        s.set_state(mmf.FIELD_U, U)
+        Uo, Wo = U.copy(), np.zeros_like(U)
+        for _ in range(2):
+            R, me = oracle.compute_rhs(m, Uo)
+            assert s.compute_rhs(mmf.FIELD_U) == me
+            dt = oracle.choose_dt(0.45, m["h"], me, 0.0, 4.0)
+            oracle.rk_stage(m, 1, dt, Uo, Wo, R); s.rk_stage(1, dt)
+            R, me = oracle.compute_rhs(m, Wo)
+            assert s.compute_rhs(mmf.FIELD_W) == me
+            oracle.rk_stage(m, 2, dt, Uo, Wo, R); s.rk_stage(2, dt)
+            R, me = oracle.compute_rhs(m, Wo)
+            assert s.compute_rhs(mmf.FIELD_W) == me
+            oracle.rk_stage(m, 3, dt, Uo, Wo, R); s.rk_stage(3, dt)
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+
+
+@pytest.mark.parametrize("case", GOLDEN_3D, ids=lambda c: c["name"])
+def test_reference_golden_strings_uniform_path(mmf, oracle, case):
+    m = oracle.problem_mesh(case["problem"], 3, case["n_cells"])
+    t_end = case["t_end"] if case["t_end"] >= 0 else oracle.end_time(case["problem"], 3)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+        s.set_state(mmf.FIELD_U, oracle.init_state(m))
+        t, steps = s.run(case["cfl"], m["h"], 0.0, t_end)
+        U = s.get_state(mmf.FIELD_U)
+    assert steps == case["steps"] and t == t_end
+    assert oracle_lib.format_error(oracle.error_norm(m, U, t_end)) == case["expected"]
+    ref = oracle.run(case["problem"], 3, case["n_cells"], t_end=case["t_end"], cfl=case["cfl"], want_state=True)
+    assert bits_equal(U, ref["U"])
+
+
+def test_compact_descriptor_equals_full_descriptor(mmf, oracle):
+    """mmf_create_uniform (no connectivity arrays) == mmf_create(full description)."""
+    m = oracle.problem_mesh("radsod", 3, 32)
+    U = oracle.init_state(m)
+    with mmf.EulerSolver.from_mesh(m) as a, mmf.EulerSolver.uniform((32, 32, 32), m["h"], _bc_sides(m)) as b:
+        for s in (a, b):
+            s.set_state(mmf.FIELD_U, U)
+        ta, na = a.run(0.45, m["h"], 0.0, 1e30, max_steps=6)
+        tb, nb = b.run(0.45, m["h"], 0.0, 1e30, max_steps=6)
+        assert (ta, na) == (tb, nb)
+        assert bits_equal(a.get_state(mmf.FIELD_U), b.get_state(mmf.FIELD_U))
+
+
+def test_lexicographic_numbering_non_cubic_box(mmf, oracle):
+    """Non-cubic, non-power-of-two box numbered lexicographically: uniform path must detect the
+    numbering and stay bit-exact; ragged tiles in x (37 = 30 + 7) and y."""
+    m = lexicographic_box_mesh(37, 19, 11, 0.125, 1)
+    m["problem"] = "radsod"
+    rng = np.random.default_rng(11)
+    nc = m["volume"].shape[0]
+    rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-1, 1, (nc, 3)); p = rng.uniform(0.5, 1.5, nc)
+    U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        info = s.info()
+        assert info["path"] == mmf.PATH_UNIFORM and info["order_exact"] == 1
+        s.set_state(mmf.FIELD_U, U)
+        ref, ref_eig = oracle.compute_rhs(m, U)
+        assert s.compute_rhs(mmf.FIELD_U) == ref_eig
+        assert bits_equal(s.get_state(mmf.FIELD_RHS), ref)
+        t = 0.0
+        for _ in range(4):
+            dto, _ = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+            dtg, _ = s.step(0.45, 0.125, t, 1e30)
+            assert dtg == dto
+            t += dto
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+
+
+def test_axis_order_flag_is_within_tolerance_not_exact(mmf, oracle):
+    """MMF_FLAG_ORDER_AXIS trades the host's accumulation order for a fixed one: results move by
+    rounding only (north_star tolerance 1e-12 relative)."""
+    m = oracle.problem_mesh("vortex_xy", 3, 32)
+    U = oracle.init_state(m)
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    with mmf.EulerSolver.from_mesh(m, flags=mmf.FLAG_ORDER_AXIS) as s:
+        assert s.info()["order_exact"] == 0
+        s.set_state(mmf.FIELD_U, U)
+        t = 0.0
+        for _ in range(10):
+            dto, _ = oracle.step(m, 0.45, t, 2.0, Uo, Wo, Ro)
+            s.step(0.45, m["h"], t, 2.0)
+            t += dto
+        assert max_rel_diff(s.get_state(mmf.FIELD_U), Uo) <= 1e-12
+
+
+def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle):
+    boxes = np.array([[3.0, 3.0, 3.0, 5.0, 5.0, 5.0]])
+    m = oracle.problem_mesh("radsod", 3, 16, boxes=boxes)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_GENERIC
+
+
+def test_large_mesh_properties(mmf):
+    """Full benchmark size (256^3): properties that need no oracle.
+    (1) a uniform free-stream state is a fixed point of the scheme (every interface flux cancels);
+    (2) the total of each conserved variable changes only by the boundary fluxes: with a vortex
+        that is still far from the free-flow borders, mass/momentum/energy are conserved to rounding;
+    (3) the run is deterministic (no atomics on data): two runs give identical bits."""
+    n, L = 256, 10.0
+    h = L / n
+    with mmf.EulerSolver.uniform((n, n, n), h, [0] * 6, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC,
+                                 interface_numbering=mmf.NUMBERING_MORTON) as s:
+        rho, u, v, w, p = 1.0, 1.0, 1.0, 0.0, 1.0
+        U = np.empty((n ** 3, 5))
+        U[:] = [rho, rho * u, rho * v, rho * w, p / 0.4 + 0.5 * rho * (u * u + v * v + w * w)]
+        s.set_state(mmf.FIELD_U, U)
+        s.run(0.45, h, 0.0, 1e30, max_steps=2)
+        out = s.get_state(mmf.FIELD_U)
+        assert max_rel_diff(out, U) <= 1e-14
+        # isentropic vortex centred in the box
+        x = (np.arange(n) + 0.5) * h - 5.0
+        X, Y = np.meshgrid(x, x, indexing="xy")
+        r2 = X * X + Y * Y
+        shape = 5.0 / (2 * np.pi) * np.exp(0.5 * (1 - r2))
+        T = 1.0 - 0.4 / 2.8 * shape * shape
+        pp = T ** 3.5
+        rr = pp / T
+        uu, vv = 1.0 - Y * shape, 1.0 + X * shape
+        plane = np.stack([rr, rr * uu, rr * vv, 0 * rr, pp / 0.4 + 0.5 * rr * (uu * uu + vv * vv)], axis=-1)
+        U = np.broadcast_to(plane[None], (n, n, n, 5)).reshape(-1, 5).copy()
+        s.set_state(mmf.FIELD_U, U)
+        s.run(0.45, h, 0.0, 1e30, max_steps=3)
+        a = s.get_state(mmf.FIELD_U).copy()
+        tot0, tot1 = U.sum(0), a.sum(0)
+        assert np.all(np.abs(tot1 - tot0) <= 1e-9 * np.abs(tot0).max())
+        assert np.isfinite(a).all() and a[:, 0].min() > 0.3
+        s.set_state(mmf.FIELD_U, U)
+        s.run(0.45, h, 0.0, 1e30, max_steps=3)
+        assert bits_equal(s.get_state(mmf.FIELD_U), a)
