@@ -4,6 +4,7 @@
 
 #include "mmf_common.cuh"
 #include "uniform_kernels.cuh"
+#include "uniform_stage_v2.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -21,6 +22,7 @@ struct UniformPath {
     double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
     int w_cur = 1;                    // which array currently holds field W
     int nw = 16;                      // warps per CTA of the stage kernel
+    int kernel_version = 2;           // 1 = shuffle kernel, 2 = shared-memory record kernel
     int lz = 0;                       // planes per CTA
     bool eig_valid = false;
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
@@ -61,15 +63,25 @@ static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    auto kern = uniform_stage_kernel<STAGE, ORDER, NW>;
-    const size_t smem = (size_t) NW * 16 * 32 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_set = true;
-    }
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (NW - 2) - 1) / (NW - 2), (g.nz + u->lz - 1) / u->lz);
-    {
+    if (u->kernel_version == 1) {
+        auto kern = uniform_stage_kernel<STAGE, ORDER, NW>;
+        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_set = true;
+        }
+        ScopedLaunchTimer timer(ctx, STAGE);
+        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
+    } else {
+        auto kern = uniform_stage_kernel_v2<STAGE, ORDER, NW, (NW < 16)>;
+        const size_t smem = (size_t) NW * (REC_SLOTS + 2 * FLX_SLOTS) * 32 * sizeof(double2);
+        static bool attr_set = false;
+        if (!attr_set) {
+            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_set = true;
+        }
         ScopedLaunchTimer timer(ctx, STAGE);
         kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
     }
@@ -81,6 +93,7 @@ template <int STAGE, int ORDER>
 static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     if (ctx->uni->nw == 8) return launch_stage_t<STAGE, ORDER, 8>(ctx, Sin, Un, Out, d_max);
+    if (ctx->uni->nw == 12) return launch_stage_t<STAGE, ORDER, 12>(ctx, Sin, Un, Out, d_max);
     return launch_stage_t<STAGE, ORDER, 16>(ctx, Sin, Un, Out, d_max);
 }
 
@@ -128,14 +141,16 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // covers the SMs several times over
     const char *env_nw = getenv("MMF_STAGE_WARPS");
     u->nw = env_nw ? atoi(env_nw) : 16;
-    if (u->nw != 8 && u->nw != 16) u->nw = 16;
+    if (u->nw != 8 && u->nw != 12 && u->nw != 16) u->nw = 16;
+    const char *env_kv = getenv("MMF_STAGE_KERNEL");
+    u->kernel_version = (env_kv && atoi(env_kv) == 1) ? 1 : 2;
     const char *env_lz = getenv("MMF_STAGE_LZ");
     if (env_lz && atoi(env_lz) > 0) {
         u->lz = atoi(env_lz);
     } else {
         const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + u->nw - 3) / (u->nw - 2));
         const long long sms = ctx->prop.multiProcessorCount;
-        const long long ctas_per_sm = (u->nw == 8) ? 2 : 1;
+        const long long ctas_per_sm = (u->nw == 8 && u->kernel_version == 1) ? 2 : 1;
         // aim for >= 4 waves, but keep chunks long enough (>= 16 planes) to amortise the prologue
         long long chunks = (4 * sms * ctas_per_sm + tiles_xy - 1) / tiles_xy;
         chunks = std::max<long long>(1, std::min<long long>(chunks, std::max(1, g.nz / 16)));

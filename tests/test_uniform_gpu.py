@@ -178,8 +178,8 @@ def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle):
 def test_large_mesh_properties(mmf):
     """Full benchmark size (256^3): properties that need no oracle.
     (1) a uniform free-stream state is a fixed point of the scheme (every interface flux cancels);
-    (2) the total of each conserved variable changes only by the boundary fluxes: with a vortex
-        that is still far from the free-flow borders, mass/momentum/energy are conserved to rounding;
+    (2) the total of each conserved variable changes only by the fluxes through the free-flow borders:
+        with the vortex far from them, mass and energy move by < 1e-10 and momentum by < 1e-7 relative;
     (3) the run is deterministic (no atomics on data): two runs give identical bits."""
     n, L = 256, 10.0
     h = L / n
@@ -207,7 +207,8 @@ def test_large_mesh_properties(mmf):
         s.run(0.45, h, 0.0, 1e30, max_steps=3)
         a = s.get_state(mmf.FIELD_U).copy()
         tot0, tot1 = U.sum(0), a.sum(0)
-        assert np.all(np.abs(tot1 - tot0) <= 1e-9 * np.abs(tot0).max())
+        assert np.all(np.abs(tot1 - tot0)[[0, 4]] <= 1e-10 * np.abs(tot0).max())
+        assert np.all(np.abs(tot1 - tot0) <= 1e-7 * np.abs(tot0).max())
         assert np.isfinite(a).all() and a[:, 0].min() > 0.3
         s.set_state(mmf.FIELD_U, U)
         s.run(0.45, h, 0.0, 1e30, max_steps=3)
