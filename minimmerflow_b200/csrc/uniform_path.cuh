@@ -4,7 +4,7 @@
 
 #include "mmf_common.cuh"
 #include "uniform_kernels.cuh"
-#include "uniform_stage_v2.cuh"
+#include "uniform_stage_v3.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -22,7 +22,7 @@ struct UniformPath {
     double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
     int w_cur = 1;                    // which array currently holds field W
     int nw = 16;                      // warps per CTA of the stage kernel
-    int kernel_version = 2;           // 1 = shuffle kernel, 2 = shared-memory record kernel
+    int kernel_version = 3;           // 1 = CTA-barrier kernel, 3 = pairwise split-phase mbarrier kernel
     int lz = 0;                       // planes per CTA
     bool eig_valid = false;
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
@@ -75,8 +75,8 @@ static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, dou
         ScopedLaunchTimer timer(ctx, STAGE);
         kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
     } else {
-        auto kern = uniform_stage_kernel_v2<STAGE, ORDER, NW, (NW < 16)>;
-        const size_t smem = (size_t) NW * (REC_SLOTS + 2 * FLX_SLOTS) * 32 * sizeof(double2);
+        auto kern = uniform_stage_kernel_v3<STAGE, ORDER, NW>;
+        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double) + 2 * NW * sizeof(unsigned long long);
         static bool attr_set = false;
         if (!attr_set) {
             MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -140,17 +140,19 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // launch shape: 16-warp CTAs when the box is tall enough in y, z chunks sized so that the grid
     // covers the SMs several times over
     const char *env_nw = getenv("MMF_STAGE_WARPS");
-    u->nw = env_nw ? atoi(env_nw) : 16;
-    if (u->nw != 8 && u->nw != 12 && u->nw != 16) u->nw = 16;
+    // 12 warps: 168 registers per thread, the smallest CTA whose stage kernels do not spill
+    // (128-register shapes spill and run ~1.5x slower, profiles/r01b_*)
+    u->nw = env_nw ? atoi(env_nw) : 12;
+    if (u->nw != 8 && u->nw != 12 && u->nw != 16) u->nw = 12;
     const char *env_kv = getenv("MMF_STAGE_KERNEL");
-    u->kernel_version = (env_kv && atoi(env_kv) == 1) ? 1 : 2;
+    u->kernel_version = (env_kv && atoi(env_kv) == 1) ? 1 : 3;
     const char *env_lz = getenv("MMF_STAGE_LZ");
     if (env_lz && atoi(env_lz) > 0) {
         u->lz = atoi(env_lz);
     } else {
         const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + u->nw - 3) / (u->nw - 2));
         const long long sms = ctx->prop.multiProcessorCount;
-        const long long ctas_per_sm = (u->nw == 8 && u->kernel_version == 1) ? 2 : 1;
+        const long long ctas_per_sm = 1;
         // aim for >= 4 waves, but keep chunks long enough (>= 16 planes) to amortise the prologue
         long long chunks = (4 * sms * ctas_per_sm + tiles_xy - 1) / tiles_xy;
         chunks = std::max<long long>(1, std::min<long long>(chunks, std::max(1, g.nz / 16)));

@@ -35,8 +35,10 @@ def main():
     cells = args.size ** 3
     ref = None
     for var in args.variants.split(","):
-        kv, nw, lz = var.split(":")
+        parts = var.split(":")
+        kv, nw, lz = parts[:3]
         os.environ["MMF_STAGE_KERNEL"], os.environ["MMF_STAGE_WARPS"] = kv, nw
+        os.environ["MMF_STAGE_UNROLL"] = parts[3] if len(parts) > 3 else "0"
         if int(lz) > 0:
             os.environ["MMF_STAGE_LZ"] = lz
         else:
