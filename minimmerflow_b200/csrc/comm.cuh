@@ -114,10 +114,10 @@ static void comm_destroy(mmf_ctx *ctx)
 }
 
 // MPI_Allreduce(MPI_IN_PLACE, &maxEig, 1, MPI_DOUBLE, MPI_MAX) of src/main.cpp:393, in stream
-int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value)
+int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value, int count)
 {
     Comm *c = ctx->comm;
-    MMF_NCCL(ctx, nccl_api().AllReduce(d_value, d_value, 1, ncclDouble, ncclMax, c->comm, ctx->stream));
+    MMF_NCCL(ctx, nccl_api().AllReduce(d_value, d_value, (size_t) count, ncclDouble, ncclMax, c->comm, ctx->stream));
     return MMF_OK;
 }
 

@@ -440,7 +440,7 @@ static int step_enqueue(mmf_ctx *ctx)
     if (ctx->path == MMF_PATH_UNIFORM) return uniform_step(ctx);
     // unfused reference-shaped sequence (src/main.cpp:383-506)
     if ((rc = rhs_enqueue(ctx, MMF_FIELD_U, 0))) return rc;
-    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0]))) return rc;
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0], 1))) return rc;
     choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
     MMF_LAUNCH_CHECK(ctx);
     if ((rc = rk_enqueue(ctx, 1))) return rc;
@@ -451,6 +451,7 @@ static int step_enqueue(mmf_ctx *ctx)
     if ((rc = rhs_enqueue(ctx, MMF_FIELD_W, 2))) return rc;
     if ((rc = rk_enqueue(ctx, 3))) return rc;
     if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_U))) return rc;
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[1], 2))) return rc; // logged only (:436, :472)
     advance_time_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -578,7 +579,7 @@ extern "C" int mmf_allreduce_max(mmf_ctx *ctx, double *value)
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->h_ctl->max_eig[0] = *value;
     MMF_CUDA(ctx, cudaMemcpyAsync(&ctx->d_ctl->max_eig[0], &ctx->h_ctl->max_eig[0], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0]))) return rc;
+    if ((rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0], 1))) return rc;
     MMF_CUDA(ctx, cudaMemcpyAsync(&ctx->h_ctl->max_eig[0], &ctx->d_ctl->max_eig[0], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *value = ctx->h_ctl->max_eig[0];

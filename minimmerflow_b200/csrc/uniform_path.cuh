@@ -415,7 +415,7 @@ static int uniform_rk(mmf_ctx *ctx, int stage)
     return uniform_refresh_ghosts(ctx, stage == 3 ? U : W, 0);
 }
 
-int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value); // comm.cuh
+int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value, int count); // comm.cuh
 
 // One fused SSP-RK3 step (replaces src/main.cpp:383-506):
 //   max eigenvalue of U -> dt on the device -> three fused residual+update kernels, each followed
@@ -430,11 +430,11 @@ static int uniform_step(mmf_ctx *ctx)
 
     MMF_CUDA(ctx, cudaMemsetAsync(&c->max_eig[0], 0, 4 * sizeof(double), ctx->stream));
     {
-        dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2);
+        dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
         uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
         MMF_LAUNCH_CHECK(ctx);
     }
-    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0]))) return rc;
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
     choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
     MMF_LAUNCH_CHECK(ctx);
 
@@ -447,6 +447,8 @@ static int uniform_step(mmf_ctx *ctx)
     if ((rc = launch_stage<3>(ctx, Wb, U, U, &c->max_eig[2]))) return rc;
     if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
     u->w_cur = 2;
+    // the two values main.cpp only logs (:436, :472)
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[1], 2))) return rc;
     advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c);
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;

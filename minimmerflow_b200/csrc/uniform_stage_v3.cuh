@@ -11,7 +11,8 @@
 //     the x faces), and only then waits;
 //   * the two halo rows run their own lean loops (state, y flux, nothing else);
 //   * masks for the max-eigenvalue reduction are loop-invariant and applied once at the end.
-// Bit-identical to v1 and to the oracle (tests/test_uniform_gpu.py runs every kernel version).
+// Bit-identical to v1 and to the CPU restatement of the reference (tests/test_uniform_gpu.py runs
+// every kernel version).
 #pragma once
 
 #include "uniform_kernels.cuh"

@@ -1,0 +1,104 @@
+"""Two-GPU parity (one process per GPU, NCCL over NVLink), through the C-ABI.
+
+(1) uniform path: the 32^3 cube split into two z boxes (the Morton chunks of a 2-rank partition);
+(2) generic path: Morton-chunk partition with one ghost layer and explicit send / receive lists
+    (the role of GhostCommunicator, src/communications.cpp:609-741).
+Both must reproduce the SERIAL oracle bit for bit on every rank's interior cells -- the reference
+expects the same golden string from 1 and 3 ranks (test/<case>/CMakeLists.txt:36-40)."""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from common import bits_equal
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _share_unique_id(mmf, rank, path):
+    if rank == 0:
+        uid = mmf.EulerSolver.comm_unique_id()
+        with open(path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(path + ".tmp", path)
+        return uid
+    for _ in range(600):
+        if os.path.exists(path):
+            return open(path, "rb").read()
+        time.sleep(0.05)
+    raise RuntimeError("no NCCL unique id")
+
+
+def _worker(rank, world, mode, problem, n, steps, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import minimmerflow_b200 as mmf
+    from minimmerflow_b200.partition import box_decomposition, box_of_rank, morton_chunk_partition
+    orc = oracle_lib.load()
+    m = orc.problem_mesh(problem, 3, n)
+    U = orc.init_state(m)
+    uid = _share_unique_id(mmf, rank, os.path.join(out_dir, f"uid_{mode}"))
+    h = m["h"]
+    if mode == "uniform":
+        grid = box_decomposition(world)
+        dims = (n // grid[0], n // grid[1], n // grid[2])
+        offset, nbrs = box_of_rank(rank, grid, dims)
+        ijk = m["cell_ijk"]
+        mine = np.all((ijk >= np.array(offset)) & (ijk < np.array(offset) + np.array(dims)), axis=1)
+        loc = ijk[mine] - np.array(offset)
+        order = np.argsort((loc[:, 2] * dims[1] + loc[:, 1]) * dims[0] + loc[:, 0])   # lexicographic in the box
+        gids = np.nonzero(mine)[0][order]
+        bc = int(m["bc"][m["neigh"] < 0][0])
+        s = mmf.EulerSolver.uniform(dims, h, [bc] * 6, device=rank, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC,
+                                    interface_numbering=mmf.NUMBERING_MORTON, global_dims=(n, n, n), box_offset=offset)
+        s.comm_init(rank, world, uid)
+        s.comm_set_box_neighbours(nbrs)
+        s.set_state(mmf.FIELD_U, U[gids])
+        n_int = len(gids)
+    else:
+        loc, comm = morton_chunk_partition(m, world, rank)
+        s = mmf.EulerSolver.from_mesh(loc, device=rank, flags=mmf.FLAG_FORCE_GENERIC)
+        s.comm_init(rank, world, uid)
+        s.comm_set_ghost_lists(comm["neighbours"], comm["send"], comm["recv"])
+        gids = comm["global_ids"]
+        s.set_state(mmf.FIELD_U, U[gids])
+        n_int = comm["n_internal"]
+    t = 0.0
+    dts, eigs = [], []
+    for _ in range(steps):
+        dt, me = s.step(0.45, h, t, 1e30)
+        t += dt
+        dts.append(dt); eigs.append(me)
+    out = s.get_state(mmf.FIELD_U)
+    np.save(os.path.join(out_dir, f"{mode}_U_{rank}.npy"), out[:n_int])
+    np.save(os.path.join(out_dir, f"{mode}_ids_{rank}.npy"), gids[:n_int])
+    np.save(os.path.join(out_dir, f"{mode}_dt_{rank}.npy"), np.array(dts))
+    np.save(os.path.join(out_dir, f"{mode}_eig_{rank}.npy"), np.array(eigs))
+    s.close()
+
+
+@pytest.mark.parametrize("mode,problem", [("uniform", "vortex_xy"), ("uniform", "radsod"), ("generic", "vortex_xy")])
+def test_two_gpu_run_equals_serial_oracle(mmf, oracle, tmp_path, mode, problem):
+    if mmf.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, n, steps = 2, 32, 5
+    mp.spawn(_worker, args=(world, mode, problem, n, steps, str(tmp_path)), nprocs=world, join=True)
+    m = oracle.problem_mesh(problem, 3, n)
+    Uo = oracle.init_state(m)
+    Wo, Ro = np.zeros_like(Uo), np.zeros_like(Uo)
+    t, dts, eigs = 0.0, [], []
+    for _ in range(steps):
+        dt, me3 = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+        t += dt
+        dts.append(dt); eigs.append(list(me3))
+    got = np.empty_like(Uo)
+    for r in range(world):
+        got[np.load(tmp_path / f"{mode}_ids_{r}.npy")] = np.load(tmp_path / f"{mode}_U_{r}.npy")
+        assert np.array_equal(np.load(tmp_path / f"{mode}_dt_{r}.npy"), np.array(dts))
+        assert np.array_equal(np.load(tmp_path / f"{mode}_eig_{r}.npy"), np.array(eigs))
+    assert bits_equal(got, Uo)

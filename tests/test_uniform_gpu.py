@@ -57,8 +57,10 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
         assert eig == ref_eig and bits_equal(got, ref), problem
 
 
-@pytest.mark.parametrize("warps", ["8", "16"])
-def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, warps):
+@pytest.mark.parametrize("kernel,warps", [("3", "12"), ("3", "8"), ("3", "16"), ("1", "12"), ("1", "16")])
+def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, kernel, warps):
+    """Every stage-kernel generation and CTA shape, ragged z chunks."""
+    monkeypatch.setenv("MMF_STAGE_KERNEL", kernel)
     monkeypatch.setenv("MMF_STAGE_WARPS", warps)
     monkeypatch.setenv("MMF_STAGE_LZ", "5")          # ragged z chunks on purpose
     m = oracle.problem_mesh("vortex_xy", 3, 32)
