@@ -5,6 +5,7 @@
 #include "mmf_common.cuh"
 #include "uniform_kernels.cuh"
 #include "uniform_stage_v3.cuh"
+#include "uniform_stage_v5.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -22,7 +23,8 @@ struct UniformPath {
     double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
     int w_cur = 1;                    // which array currently holds field W
     int nw = 16;                      // warps per CTA of the stage kernel
-    int kernel_version = 3;           // 1 = CTA-barrier kernel, 3 = pairwise split-phase mbarrier kernel
+    int kernel_version = 5;           // 1 = CTA-barrier kernel, 3 = pairwise split-phase mbarrier kernel,
+                                      // 5 = low-face streaming kernel (default)
     int lz = 0;                       // planes per CTA
     bool eig_valid = false;
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
@@ -74,8 +76,18 @@ static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, dou
         }
         ScopedLaunchTimer timer(ctx, STAGE);
         kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
-    } else {
+    } else if (u->kernel_version == 3) {
         auto kern = uniform_stage_kernel_v3<STAGE, ORDER, NW>;
+        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double) + 2 * NW * sizeof(unsigned long long);
+        static bool attr_set = false;
+        if (!attr_set) {
+            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_set = true;
+        }
+        ScopedLaunchTimer timer(ctx, STAGE);
+        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
+    } else {
+        auto kern = uniform_stage_kernel_v5<STAGE, ORDER, NW>;
         const size_t smem = (size_t) NW * 16 * 32 * sizeof(double) + 2 * NW * sizeof(unsigned long long);
         static bool attr_set = false;
         if (!attr_set) {
@@ -92,9 +104,13 @@ static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 template <int STAGE, int ORDER>
 static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
 {
-    if (ctx->uni->nw == 8) return launch_stage_t<STAGE, ORDER, 8>(ctx, Sin, Un, Out, d_max);
-    if (ctx->uni->nw == 12) return launch_stage_t<STAGE, ORDER, 12>(ctx, Sin, Un, Out, d_max);
-    return launch_stage_t<STAGE, ORDER, 16>(ctx, Sin, Un, Out, d_max);
+    switch (ctx->uni->nw) {
+    case 8:  return launch_stage_t<STAGE, ORDER, 8>(ctx, Sin, Un, Out, d_max);
+    case 12: return launch_stage_t<STAGE, ORDER, 12>(ctx, Sin, Un, Out, d_max);
+    case 13: return launch_stage_t<STAGE, ORDER, 13>(ctx, Sin, Un, Out, d_max);
+    case 14: return launch_stage_t<STAGE, ORDER, 14>(ctx, Sin, Un, Out, d_max);
+    default: return launch_stage_t<STAGE, ORDER, 16>(ctx, Sin, Un, Out, d_max);
+    }
 }
 
 template <int STAGE>
@@ -143,9 +159,10 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // 12 warps: 168 registers per thread, the smallest CTA whose stage kernels do not spill
     // (128-register shapes spill and run ~1.5x slower, profiles/r01b_*)
     u->nw = env_nw ? atoi(env_nw) : 12;
-    if (u->nw != 8 && u->nw != 12 && u->nw != 16) u->nw = 12;
+    if (u->nw != 8 && u->nw != 12 && u->nw != 13 && u->nw != 14 && u->nw != 16) u->nw = 12;
     const char *env_kv = getenv("MMF_STAGE_KERNEL");
-    u->kernel_version = (env_kv && atoi(env_kv) == 1) ? 1 : 3;
+    u->kernel_version = env_kv ? atoi(env_kv) : 5;
+    if (u->kernel_version != 1 && u->kernel_version != 3) u->kernel_version = 5;
     const char *env_lz = getenv("MMF_STAGE_LZ");
     if (env_lz && atoi(env_lz) > 0) {
         u->lz = atoi(env_lz);

@@ -57,7 +57,8 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
         assert eig == ref_eig and bits_equal(got, ref), problem
 
 
-@pytest.mark.parametrize("kernel,warps", [("3", "12"), ("3", "8"), ("3", "16"), ("1", "12"), ("1", "16")])
+@pytest.mark.parametrize("kernel,warps", [("5", "12"), ("5", "16"), ("5", "14"), ("5", "8"),
+                                          ("3", "12"), ("3", "8"), ("3", "16"), ("1", "12"), ("1", "16")])
 def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, kernel, warps):
     """Every stage-kernel generation and CTA shape, ragged z chunks."""
     monkeypatch.setenv("MMF_STAGE_KERNEL", kernel)
