@@ -6,6 +6,7 @@
 #include "uniform_kernels.cuh"
 #include "uniform_stage_v3.cuh"
 #include "uniform_stage_v5.cuh"
+#include "uniform_stage_v5r.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +14,15 @@
 #include <cstring>
 
 namespace mmf {
+
+// which stage-kernel form runs a stage and with how many warps per CTA:
+//   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
+//   '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check
+struct StageShape {
+    char form = 'p';
+    int nw = 16;
+    int lz = 0; // planes per CTA
+};
 
 struct UniformPath {
     UniformGeom g{};
@@ -22,10 +32,7 @@ struct UniformPath {
     int *cell_off = nullptr;          // optional explicit raw id -> padded offset
     double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
     int w_cur = 1;                    // which array currently holds field W
-    int nw = 16;                      // warps per CTA of the stage kernel
-    int kernel_version = 5;           // 1 = CTA-barrier kernel, 3 = pairwise split-phase mbarrier kernel,
-                                      // 5 = low-face streaming kernel (default)
-    int lz = 0;                       // planes per CTA
+    StageShape shape[4];              // kernel form, CTA size and z chunk per stage (0 = RHS only, 1..3)
     bool eig_valid = false;
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
@@ -60,42 +67,18 @@ static int uniform_ensure_rhs(mmf_ctx *ctx)
 
 // ---- launch helpers -----------------------------------------------------------------------------
 
-template <int STAGE, int ORDER, int NW>
-static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
+template <typename K>
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (NW - 2) - 1) / (NW - 2), (g.nz + u->lz - 1) / u->lz);
-    if (u->kernel_version == 1) {
-        auto kern = uniform_stage_kernel<STAGE, ORDER, NW>;
-        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            attr_set = true;
-        }
-        ScopedLaunchTimer timer(ctx, STAGE);
-        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
-    } else if (u->kernel_version == 3) {
-        auto kern = uniform_stage_kernel_v3<STAGE, ORDER, NW>;
-        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double) + 2 * NW * sizeof(unsigned long long);
-        static bool attr_set = false;
-        if (!attr_set) {
-            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            attr_set = true;
-        }
-        ScopedLaunchTimer timer(ctx, STAGE);
-        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
-    } else {
-        auto kern = uniform_stage_kernel_v5<STAGE, ORDER, NW>;
-        const size_t smem = (size_t) NW * 16 * 32 * sizeof(double) + 2 * NW * sizeof(unsigned long long);
-        static bool attr_set = false;
-        if (!attr_set) {
-            MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            attr_set = true;
-        }
-        ScopedLaunchTimer timer(ctx, STAGE);
-        kern<<<grid, NW * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, u->lz);
+    const int lz = u->shape[stage].lz;
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
+    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
+    MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz);
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -104,13 +87,17 @@ static int launch_stage_t(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 template <int STAGE, int ORDER>
 static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
 {
-    switch (ctx->uni->nw) {
-    case 8:  return launch_stage_t<STAGE, ORDER, 8>(ctx, Sin, Un, Out, d_max);
-    case 12: return launch_stage_t<STAGE, ORDER, 12>(ctx, Sin, Un, Out, d_max);
-    case 13: return launch_stage_t<STAGE, ORDER, 13>(ctx, Sin, Un, Out, d_max);
-    case 14: return launch_stage_t<STAGE, ORDER, 14>(ctx, Sin, Un, Out, d_max);
-    default: return launch_stage_t<STAGE, ORDER, 16>(ctx, Sin, Un, Out, d_max);
+    UniformPath *u = ctx->uni;
+    const StageShape sh = u->shape[STAGE];
+    if (sh.form == '3') return launch_stage_k(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
+    if (sh.form == 'r') {
+        if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
+        if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
+        return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
     }
+    if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
+    if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
+    return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
 }
 
 template <int STAGE>
@@ -153,27 +140,45 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         fill_benign_kernel<<<grid_for(g.fs, 256), 256, 0, ctx->stream>>>(u->arr[a], g.fs);
         MMF_LAUNCH_CHECK(ctx);
     }
-    // launch shape: 16-warp CTAs when the box is tall enough in y, z chunks sized so that the grid
-    // covers the SMs several times over
-    const char *env_nw = getenv("MMF_STAGE_WARPS");
-    // 12 warps: 168 registers per thread, the smallest CTA whose stage kernels do not spill
-    // (128-register shapes spill and run ~1.5x slower, profiles/r01b_*)
-    u->nw = env_nw ? atoi(env_nw) : 12;
-    if (u->nw != 8 && u->nw != 12 && u->nw != 13 && u->nw != 14 && u->nw != 16) u->nw = 12;
-    const char *env_kv = getenv("MMF_STAGE_KERNEL");
-    u->kernel_version = env_kv ? atoi(env_kv) : 5;
-    if (u->kernel_version != 1 && u->kernel_version != 3) u->kernel_version = 5;
+    // Launch shapes, measured at 256^3 on B200 (profiles/): the ping-pong form at 16 warps (128
+    // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (166 registers,
+    // no spills) the fastest for stages 2 and 3, which also stream U^n.
+    // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "312" = v3 everywhere.
+    const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
+    for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];
+    if (const char *cfg = getenv("MMF_STAGE_CFG")) {
+        int st = 0;
+        for (const char *p = cfg; *p && st < 4;) {
+            StageShape sh;
+            sh.form = *p++;
+            sh.nw = atoi(p);
+            while (*p && *p != ':') ++p;
+            const bool last = (*p == 0);
+            if (*p == ':') ++p;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if (sh.form == '3') sh.nw = 12;
+            u->shape[st++] = sh;
+            if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
+        }
+    }
+    // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
+    // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
+    // derives for its first z interface; chunks stay between 16 and 96 planes.
     const char *env_lz = getenv("MMF_STAGE_LZ");
-    if (env_lz && atoi(env_lz) > 0) {
-        u->lz = atoi(env_lz);
-    } else {
-        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + u->nw - 3) / (u->nw - 2));
-        const long long sms = ctx->prop.multiProcessorCount;
-        const long long ctas_per_sm = 1;
-        // aim for >= 4 waves, but keep chunks long enough (>= 16 planes) to amortise the prologue
-        long long chunks = (4 * sms * ctas_per_sm + tiles_xy - 1) / tiles_xy;
-        chunks = std::max<long long>(1, std::min<long long>(chunks, std::max(1, g.nz / 16)));
-        u->lz = (int) ((g.nz + chunks - 1) / chunks);
+    for (int st = 0; st < 4; ++st) {
+        StageShape &sh = u->shape[st];
+        if (env_lz && atoi(env_lz) > 0) { sh.lz = atoi(env_lz); continue; }
+        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.nw - 3) / (sh.nw - 2));
+        const double sms = (double) ctx->prop.multiProcessorCount;
+        double best = -1.;
+        for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 16); ++chunks) {
+            const int lz = (g.nz + chunks - 1) / chunks;
+            const long long n_chunks = (g.nz + lz - 1) / lz;
+            const double waves = (double) (tiles_xy * n_chunks) / sms;
+            const double score = waves / std::ceil(waves) * (double) lz / (lz + 1.0);
+            if (score > best + 1e-9) { best = score; sh.lz = lz; }
+        }
+        if (sh.lz <= 0) sh.lz = g.nz;
     }
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMF_OK;

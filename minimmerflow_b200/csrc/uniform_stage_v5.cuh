@@ -17,7 +17,11 @@
 //   * that brings the kernel under 128 registers: 16 warps per SM instead of 12.
 //   * mbarriers take ONE arrival (elected lane after __syncwarp) instead of 32 same-address ones.
 //   * halo rows prefetch their loads one plane ahead.
-//   * the first and last plane are peeled out of the steady-state loop.
+//   * the first and last plane are peeled out of the steady-state loop, which is unrolled by two
+//     over a ping-pong pair of plane states: no register rotation (~65 moves per plane in v3, and
+//     ptxas liked to place the copy of the prefetched plane right behind its own load, so that
+//     every plane stalled on DRAM latency).  The single-body "rotate" form is kept in
+//     uniform_stage_v5r.cuh because it schedules better for stages 2 and 3 (see there).
 // Arithmetic per value is the same sequence of IEEE operations as in v1/v3 (same helpers), so the
 // results stay bit-identical to the CPU restatement of the reference (tests/test_uniform_gpu.py).
 #pragma once
@@ -62,6 +66,158 @@ __device__ __forceinline__ void finish_plane(const double *S, const double *AFz,
         if (pred) op[k * fs] = out;
     }
 }
+
+// state of one plane of one cell as it travels through two iterations
+struct PlaneState {
+    double U[NF];   // residual input of the plane
+    double Fz[NF];  // z flux of the cell, lam_z below
+    double lz;
+    double S[NF];   // running residual: everything except -z_hi
+    double Un[NF];  // U^n of the plane (stages 2, 3)
+};
+
+// everything an update row needs per plane that does not change from plane to plane
+template <int STAGE, int ORDER>
+struct RowCtx {
+    bool upd;
+    int lane, key_x, key_y, gz0;
+    double dt, Ah, volume;
+    DivConsts dc;
+    long long fs, plane;
+    double *d_own, *f_own;
+    const double *d_dn, *f_up;
+    unsigned long long *barD_own, *barD_dn, *barF_own, *barF_up;
+    const double *sp, *unp;
+    double *op;
+    double lmx, lmy, lmz;
+
+    // One plane.  On entry P is the finished state of plane kz-1 (S lacks -z_hi) and C.U holds
+    // plane kz; on exit C is the finished state of plane kz and P.U holds plane kz+1.
+    __device__ __forceinline__ void body(PlaneState &P, PlaneState &C, int kz, int z0)
+    {
+        const unsigned par = (unsigned) ((kz - z0) & 1);
+        if (STAGE >= 2 && upd) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) C.Un[k] = unp[k * fs];
+        }
+        unp += plane;
+
+        CellPrim q;
+        derive_cell(C.U, dc, q);
+
+        // ---- y record for row+1 (the earlier it is out, the less row+1 waits) -------------------------
+        double cFy[NF], cly;
+        axis_flux<1>(q, cFy, cly);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) { d_own[k * 32] = C.U[k]; d_own[(NF + k) * 32] = cFy[k]; }
+        d_own[10 * 32] = cly;
+        mbar_arrive_elect(barD_own, lane);
+
+        // ---- z interface (kz-1 | kz): completes plane kz-1 --------------------------------------------
+        double AFz[NF];
+        axis_flux<2>(q, C.Fz, C.lz);
+        {
+            const double lam = llf_area_flux(P.U, P.Fz, P.lz, C.U, C.Fz, C.lz, Ah, AFz);
+            lmz = (lam < lmz) ? lmz : lam;
+        }
+        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd && kz > z0);
+        op += plane;
+
+        // ---- plane kz+1 (<= nz, exists in the padded array) into the registers plane kz-1 just left ----
+        sp += plane;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) P.U[k] = sp[k * fs];
+
+        // ---- x interface (i-1 | i): lane-1's state by warp shuffle -------------------------------------
+        double AFx[NF];
+        {
+            double cFx[NF], clx, lU[NF], lF[NF];
+            axis_flux<0>(q, cFx, clx);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { lU[k] = shfl_up_d(C.U[k]); lF[k] = shfl_up_d(cFx[k]); }
+            const double ll  = shfl_up_d(clx);
+            const double lam = llf_area_flux(lU, lF, ll, C.U, cFx, clx, Ah, AFx);
+            lmx = (lam < lmx) ? lmx : lam;
+        }
+
+        // ---- y interface (j-1 | j): row-1's record through shared memory ------------------------------
+        double AFy[NF];
+        mbar_wait(barD_dn, par);
+        {
+            double lU[NF], lF[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
+            const double ll  = d_dn[10 * 32];
+            const double lam = llf_area_flux(lU, lF, ll, C.U, cFy, cly, Ah, AFy);
+            lmy = (lam < lmy) ? lmy : lam;
+            // row-1 published record `it` only after it had read this row's flux `it-1`
+#pragma unroll
+            for (int k = 0; k < NF; ++k) f_own[k * 32] = AFy[k];
+            mbar_arrive_elect(barF_own, lane);
+        }
+
+        // ---- ordered accumulation (src/euler.cpp:153, 237-247) ----------------------------------------
+        // interior low faces first, sorted by their creator (largest key first; a+b commutes, so only
+        // the LAST one matters); then the cell's own faces in the order it created them:
+        // (-x if border) +x (-y if border) +y (-z if border) +z; low faces `+=`, high faces `-=`.
+        const int key_z = order_key<ORDER>(gz0 + kz, 2);
+        const bool edge = (key_y < 0) | (key_z < 0); // warp-uniform: one row, one plane per warp
+        if (ORDER == NUM_AXIS) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) C.S[k] = 0.0 + AFx[k];
+        } else if (!edge) {
+            // a border low face in x alone is simply "last" (key -1), directly followed by -x_hi
+            const int last = (key_x < key_y) ? ((key_x < key_z) ? 0 : 2) : ((key_y < key_z) ? 1 : 2);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                const double p = (last == 0) ? AFy[k] : AFx[k];
+                const double t = (last == 2) ? AFy[k] : AFz[k];
+                const double r = (last == 0) ? AFx[k] : (last == 1) ? AFy[k] : AFz[k];
+                C.S[k] = (p + t) + r;
+            }
+        } else {
+            // low y / low z side of the domain: those faces enter after -x_hi, see below
+            const bool bx = key_x < 0;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                double s = 0.0; // at most two interior low faces remain: their order is immaterial
+                if (!bx) s += AFx[k];
+                if (key_y >= 0) s += AFy[k];
+                if (key_z >= 0) s += AFz[k];
+                if (bx) s += AFx[k];
+                C.S[k] = s;
+            }
+        }
+        // -x_hi: the low x face of lane+1
+#pragma unroll
+        for (int k = 0; k < NF; ++k) C.S[k] -= shfl_down_d(AFx[k]);
+        if (ORDER == NUM_AXIS || (edge && key_y < 0)) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) C.S[k] += AFy[k];
+        }
+        // -y_hi: the low y face of row+1
+        mbar_wait(barF_up, par);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) C.S[k] -= f_up[k * 32];
+        if (ORDER == NUM_AXIS || (edge && key_z < 0)) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) C.S[k] += AFz[k];
+        }
+        // -z_hi follows in the next iteration (or the epilogue)
+    }
+
+    // plane z1 only closes the last z interface
+    __device__ __forceinline__ void epilogue(PlaneState &P, const double *nU)
+    {
+        CellPrim q;
+        derive_cell(nU, dc, q);
+        double cFz[NF], clz, AFz[NF];
+        axis_flux<2>(q, cFz, clz);
+        const double lam = llf_area_flux(P.U, P.Fz, P.lz, nU, cFz, clz, Ah, AFz);
+        lmz = (lam < lmz) ? lmz : lam;
+        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd);
+    }
+};
 
 template <int STAGE, int ORDER, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -171,181 +327,65 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         lmax = yf_ok ? lmy : 0.0;
     } else {
         // ================= update rows ==============================================================
-        const bool upd   = lane >= 1 && lane <= XW && in_x && in_y;
-        const bool xf_ok = in_y && lane >= 1 && i >= 0 && i <= g.nx;                  // face (i-1 | i)
-        const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;   // face (j-1 | j)
-        const bool zf_ok = in_x && in_y;                                              // face (k-1 | k)
-        const double dt = (STAGE >= 1) ? ctl->dt : 0.0;
-        const int key_x = order_key<ORDER>(g.gx0 + i, 0);
-        const int key_y = order_key<ORDER>(g.gy0 + j, 1);
+        RowCtx<STAGE, ORDER> c;
+        c.upd   = lane >= 1 && lane <= XW && in_x && in_y;
+        c.lane  = lane;
+        c.dt    = (STAGE >= 1) ? ctl->dt : 0.0;
+        c.Ah    = Ah;
+        c.volume = g.volume;
+        c.dc    = dc;
+        c.key_x = order_key<ORDER>(g.gx0 + i, 0);
+        c.key_y = order_key<ORDER>(g.gy0 + j, 1);
+        c.gz0   = g.gz0;
+        c.fs    = fs;
+        c.plane = plane;
+        c.d_own = sm_d + row * 11 * 32 + lane;
+        c.d_dn  = sm_d + (row - 1) * 11 * 32 + lane;
+        c.f_own = sm_f + row * NF * 32 + lane;
+        c.f_up  = sm_f + (row + 1) * NF * 32 + lane;
+        c.barD_own = &barD[row];
+        c.barD_dn  = &barD[row - 1];
+        c.barF_own = &barF[row];
+        c.barF_up  = &barF[row + 1];
+        c.sp  = Sin + col + (long long) z0 * plane;        // plane z0-1
+        c.unp = Un + col + (long long) (z0 + 1) * plane;   // plane z0
+        c.op  = Out + col + (long long) z0 * plane;        // plane z0-1 (the first store goes to plane z0)
+        c.lmx = c.lmy = c.lmz = 0.0;
 
-        double *d_own = sm_d + row * 11 * 32 + lane;
-        const double *d_dn = sm_d + (row - 1) * 11 * 32 + lane;
-        double *f_own = sm_f + row * NF * 32 + lane;
-        const double *f_up = sm_f + (row + 1) * NF * 32 + lane;
-
-        const double *sp  = Sin + col + (long long) z0 * plane; // plane z0-1
-        const double *unp = Un + col + (long long) (z0 + 1) * plane; // plane z0
-        double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
-
-        double pU[NF], pFz[NF], plz, pS[NF], pUn[NF], nxt[NF];
-        double lmx = 0.0, lmy = 0.0, lmz = 0.0;
+        // Two plane states in ping-pong: after body(P, C) the roles swap, so nothing is ever copied
+        // from "current" to "previous" registers (the rotate form spends ~65 moves per plane on that,
+        // and ptxas may place the copy of the prefetched plane right behind its own load).
+        PlaneState A, B;
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) pU[k] = sp[k * fs];
-            sp += plane;
+            for (int k = 0; k < NF; ++k) A.U[k] = c.sp[k * fs];
+            c.sp += plane;
 #pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+            for (int k = 0; k < NF; ++k) B.U[k] = c.sp[k * fs];
             CellPrim q;
-            derive_cell(pU, dc, q);
-            axis_flux<2>(q, pFz, plz);
+            derive_cell(A.U, dc, q);
+            axis_flux<2>(q, A.Fz, A.lz);
 #pragma unroll
-            for (int k = 0; k < NF; ++k) { pS[k] = 0.0; pUn[k] = 0.0; }
+            for (int k = 0; k < NF; ++k) { A.S[k] = 0.0; A.Un[k] = 0.0; }
         }
-
-        for (int kz = z0; kz < z1; ++kz) {
-            const unsigned par = (unsigned) ((kz - z0) & 1);
-            double cU[NF];
-#pragma unroll
-            for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane; // plane kz+1 <= nz exists in the padded array
-#pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
-            double cUn[NF];
-            if (STAGE >= 2 && upd) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) cUn[k] = unp[k * fs];
-            }
-            unp += plane;
-
-            CellPrim q;
-            derive_cell(cU, dc, q);
-
-            // ---- y record for row+1 (the earlier it is out, the less row+1 waits) ---------------------
-            double cFy[NF], cly;
-            axis_flux<1>(q, cFy, cly);
-#pragma unroll
-            for (int k = 0; k < NF; ++k) { d_own[k * 32] = cU[k]; d_own[(NF + k) * 32] = cFy[k]; }
-            d_own[10 * 32] = cly;
-            mbar_arrive_elect(&barD[row], lane);
-
-            // ---- z interface (kz-1 | kz): completes plane kz-1 ----------------------------------------
-            double cFz[NF], clz, AFz[NF];
-            axis_flux<2>(q, cFz, clz);
-            {
-                const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
-                lmz = (lam < lmz) ? lmz : lam;
-            }
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0);
-            op += plane;
-
-            // ---- x interface (i-1 | i): lane-1's state by warp shuffle ---------------------------------
-            double AFx[NF];
-            {
-                double cFx[NF], clx, lU[NF], lF[NF];
-                axis_flux<0>(q, cFx, clx);
-#pragma unroll
-                for (int k = 0; k < NF; ++k) { lU[k] = shfl_up_d(cU[k]); lF[k] = shfl_up_d(cFx[k]); }
-                const double ll  = shfl_up_d(clx);
-                const double lam = llf_area_flux(lU, lF, ll, cU, cFx, clx, Ah, AFx);
-                lmx = (lam < lmx) ? lmx : lam;
-            }
-
-            // ---- y interface (j-1 | j): row-1's record through shared memory --------------------------
-            double AFy[NF];
-            mbar_wait(&barD[row - 1], par);
-            {
-                double lU[NF], lF[NF];
-#pragma unroll
-                for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
-                const double ll  = d_dn[10 * 32];
-                const double lam = llf_area_flux(lU, lF, ll, cU, cFy, cly, Ah, AFy);
-                lmy = (lam < lmy) ? lmy : lam;
-                // row-1 published record `it` only after it had read this row's flux `it-1`
-#pragma unroll
-                for (int k = 0; k < NF; ++k) f_own[k * 32] = AFy[k];
-                mbar_arrive_elect(&barF[row], lane);
-            }
-
-            // ---- ordered accumulation (src/euler.cpp:153, 237-247) ------------------------------------
-            // interior low faces first, sorted by their creator (largest key first; a+b commutes, so
-            // only the LAST one matters); then the cell's own faces in the order it created them:
-            // (-x if border) +x (-y if border) +y (-z if border) +z; low faces `+=`, high faces `-=`.
-            const int key_z = order_key<ORDER>(g.gz0 + kz, 2);
-            double S[NF];
-            const bool edge = (key_y < 0) | (key_z < 0); // warp-uniform: one row, one plane per warp
-            if (ORDER == NUM_AXIS) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) S[k] = 0.0 + AFx[k];
-            } else if (!edge) {
-                // a border low face in x alone is simply "last" (key -1), directly followed by -x_hi
-                const int last = (key_x < key_y) ? ((key_x < key_z) ? 0 : 2) : ((key_y < key_z) ? 1 : 2);
-#pragma unroll
-                for (int k = 0; k < NF; ++k) {
-                    const double p = (last == 0) ? AFy[k] : AFx[k];
-                    const double t = (last == 2) ? AFy[k] : AFz[k];
-                    const double r = (last == 0) ? AFx[k] : (last == 1) ? AFy[k] : AFz[k];
-                    S[k] = (p + t) + r;
-                }
-            } else {
-                // low y / low z side of the domain: those faces enter after -x_hi, see below
-                const bool bx = key_x < 0;
-#pragma unroll
-                for (int k = 0; k < NF; ++k) {
-                    double s = 0.0; // at most two interior low faces remain: their order is immaterial
-                    if (!bx) s += AFx[k];
-                    if (key_y >= 0) s += AFy[k];
-                    if (key_z >= 0) s += AFz[k];
-                    if (bx) s += AFx[k];
-                    S[k] = s;
-                }
-            }
-            // -x_hi: the low x face of lane+1
-#pragma unroll
-            for (int k = 0; k < NF; ++k) S[k] -= shfl_down_d(AFx[k]);
-            if (ORDER == NUM_AXIS) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) S[k] += AFy[k];
-            } else if (edge && key_y < 0) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) S[k] += AFy[k];
-            }
-            // -y_hi: the low y face of row+1
-            mbar_wait(&barF[row + 1], par);
-#pragma unroll
-            for (int k = 0; k < NF; ++k) S[k] -= f_up[k * 32];
-            if (ORDER == NUM_AXIS) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) S[k] += AFz[k];
-            } else if (edge && key_z < 0) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) S[k] += AFz[k];
-            }
-
-            // ---- plane kz becomes the previous plane; -z_hi follows in the next iteration -------------
-#pragma unroll
-            for (int k = 0; k < NF; ++k) { pS[k] = S[k]; pU[k] = cU[k]; pFz[k] = cFz[k]; }
-            plz = clz;
-            if (STAGE >= 2) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) pUn[k] = cUn[k];
-            }
+        int kz = z0;
+        for (; kz + 1 < z1; kz += 2) {
+            c.body(A, B, kz, z0);
+            c.body(B, A, kz + 1, z0);
         }
-
-        // ---- epilogue: plane z1 only closes the last z interface -----------------------------------
-        {
-            CellPrim q;
-            derive_cell(nxt, dc, q);
-            double cFz[NF], clz, AFz[NF];
-            axis_flux<2>(q, cFz, clz);
-            const double lam = llf_area_flux(pU, pFz, plz, nxt, cFz, clz, Ah, AFz);
-            lmz = (lam < lmz) ? lmz : lam;
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd);
+        if (kz < z1) {
+            c.body(A, B, kz, z0);
+            c.epilogue(B, A.U);
+        } else {
+            c.epilogue(A, B.U);
         }
-        lmax = xf_ok ? lmx : 0.0;
-        if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;
-        if (zf_ok) lmax = (lmz < lmax) ? lmax : lmz;
+        const bool xf_ok = in_y && lane >= 1 && i >= 0 && i <= g.nx;                  // face (i-1 | i)
+        const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;   // face (j-1 | j)
+        const bool zf_ok = in_x && in_y;                                              // face (k-1 | k)
+        lmax = xf_ok ? c.lmx : 0.0;
+        if (yf_ok) lmax = (c.lmy < lmax) ? lmax : c.lmy;
+        if (zf_ok) lmax = (c.lmz < lmax) ? lmax : c.lmz;
     }
 
     // ---- max eigenvalue: warp shuffle, block reduction, one atomic per CTA ----------------------

@@ -62,3 +62,51 @@ def lexicographic_box_mesh(nx, ny, nz, h, bc_code, origin=(0.0, 0.0, 0.0)):
                 icentroid=np.zeros((nf, 3)), volume=np.full(nc, h * h * h), size=np.full(nc, h),
                 ccentroid=cc, cell_ijk=ijk, box_dims=(nx, ny, nz), solved=np.ones(nc, np.uint8),
                 internal=np.ones(nc, np.uint8), fluid=np.ones(nc, np.uint8), h=h)
+
+
+def reference_cases():
+    with open(os.path.join(HERE, "golden", "reference_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+def reference_fields():
+    """Final fields of reference_cases() as produced by the unmodified reference
+    (tests/golden/make_reference_fields.py)."""
+    return np.load(os.path.join(HERE, "golden", "reference_fields.npz"))
+
+
+def case_mesh(oracle, case):
+    """Mesh + flags + BC table of a reference case (custom domain and bodies included), set up the
+    way src/main.cpp does."""
+    import ctypes as C
+    import oracle_lib as O
+    dim, origin, length = oracle.domain(case["problem"], case["dim"])
+    if case.get("origin") is not None:
+        origin = np.array(case["origin"], dtype=np.float64)
+    if case.get("length") is not None:
+        length = float(case["length"])
+    m = oracle.uniform_mesh(dim, origin, length, case["n_cells"])
+    nc, nf = m["volume"].shape[0], m["owner"].shape[0]
+    boxes = np.ascontiguousarray(case.get("bodies") or np.zeros((0, 6)), dtype=np.float64).reshape(-1, 6)
+    fluid = np.empty(nc, np.uint8)
+    oracle.lib.orc_fluid_flags(nc, O._p(m["ccentroid"], O._D), boxes.shape[0], O._p(boxes, O._D), O._p(fluid, O._U8))
+    bc = np.empty(nf, np.int32)
+    oracle.lib.orc_interface_bcs(O.PROBLEMS[case["problem"]], nf, O._p(m["owner"], O._I64), O._p(m["neigh"], O._I64),
+                                 O._p(m["icentroid"], O._D), O._p(fluid, O._U8), O._p(bc, O._I32))
+    m.update(problem=case["problem"], fluid=fluid, solved=fluid.copy(), internal=np.ones(nc, np.uint8), bc=bc)
+    return m
+
+
+def primitives(oracle, U):
+    """utils::conservative2primitive (src/utils.cpp:48-63) applied cell by cell -> {p,u,v,w,T}."""
+    import oracle_lib as O
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    P = np.empty_like(U)
+    for c in range(U.shape[0]):
+        oracle.lib.orc_conservative2primitive(U[c].ctypes.data_as(O._D), P[c].ctypes.data_as(O._D))
+    return P
+
+
+def dirichlet_info(case):
+    """problem::getBorderBCInfo (src/problem.cpp:450-477): only the forward-facing step sets data."""
+    return [1.0, 3.0, 0.0, 0.0, 1.0 / 1.4] if case["problem"] == "ffstep" else None

@@ -1,0 +1,32 @@
+"""GPU parity against the REFERENCE's own final fields (tests/golden/reference_fields.npz, written by
+the unmodified reference sources): the device-resident time loop (mmf_run, what replaces
+src/main.cpp:377-506) must end on bitwise the same state, after the same number of steps, on every
+case -- 2-D, bodies / BC_WALL, BC_DIRICHLET included (generic path) and the plain 3-D boxes (fused
+uniform path)."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from common import bits_equal, case_mesh, dirichlet_info, primitives, reference_cases, reference_fields
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", reference_cases(), ids=lambda c: c["name"])
+def test_resident_run_matches_reference_fields(mmf, oracle, case):
+    ref = reference_fields()
+    n = case["name"]
+    m = case_mesh(oracle, case)
+    with mmf.EulerSolver.from_mesh(m, dirichlet_info=dirichlet_info(case)) as s:
+        plain_box = m["dim"] == 3 and not case.get("bodies")
+        assert s.info()["path"] == (mmf.PATH_UNIFORM if plain_box else mmf.PATH_GENERIC)
+        s.set_state(mmf.FIELD_U, oracle.init_state(m))
+        t, steps = s.run(case["cfl"], float(m["size"].min()), 0.0, case["t_end"])
+        U = s.get_state(mmf.FIELD_U)
+    assert steps == int(ref[n + "/steps"]) and t == case["t_end"]
+    assert oracle_lib.format_error(oracle.error_norm(m, U, case["t_end"])) == str(ref[n + "/final_error"])
+    P = primitives(oracle, U)
+    assert bits_equal(ref[n + "/density"], U[:, 0])
+    assert bits_equal(ref[n + "/velocity"], P[:, 1:4])
+    assert bits_equal(ref[n + "/pressure"], P[:, 0])
+    assert bits_equal(ref[n + "/temperature"], P[:, 4])

@@ -57,12 +57,11 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
         assert eig == ref_eig and bits_equal(got, ref), problem
 
 
-@pytest.mark.parametrize("kernel,warps", [("5", "12"), ("5", "16"), ("5", "14"), ("5", "8"),
-                                          ("3", "12"), ("3", "8"), ("3", "16"), ("1", "12"), ("1", "16")])
-def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, kernel, warps):
-    """Every stage-kernel generation and CTA shape, ragged z chunks."""
-    monkeypatch.setenv("MMF_STAGE_KERNEL", kernel)
-    monkeypatch.setenv("MMF_STAGE_WARPS", warps)
+@pytest.mark.parametrize("cfg", ["", "p12", "p16", "p8", "r12", "r16", "r8", "312", "r8:p12:r16:p8"])
+def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg):
+    """Every stage-kernel form and CTA shape (default mix first), ragged z chunks."""
+    if cfg:
+        monkeypatch.setenv("MMF_STAGE_CFG", cfg)
     monkeypatch.setenv("MMF_STAGE_LZ", "5")          # ragged z chunks on purpose
     m = oracle.problem_mesh("vortex_xy", 3, 32)
     U = oracle.init_state(m)

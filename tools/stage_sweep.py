@@ -29,16 +29,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--variants", default="1:16:0,2:16:0,2:12:0,2:8:0")
+    ap.add_argument("--variants", default="p16:p16:r12:r12,p12,r12,p16,r16,312")
     args = ap.parse_args()
     U, h = vortex(args.size)
     cells = args.size ** 3
     ref = None
     for var in args.variants.split(","):
-        parts = var.split(":")
-        kv, nw, lz = parts[:3]
-        os.environ["MMF_STAGE_KERNEL"], os.environ["MMF_STAGE_WARPS"] = kv, nw
-        os.environ["MMF_STAGE_UNROLL"] = parts[3] if len(parts) > 3 else "0"
+        cfg, lz = var.split("@") if "@" in var else (var, "0")   # e.g. p16:p16:r12:r12@43
+        os.environ["MMF_STAGE_CFG"] = cfg
         if int(lz) > 0:
             os.environ["MMF_STAGE_LZ"] = lz
         else:
