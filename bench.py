@@ -35,7 +35,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--size", type=int, default=256, help="cells per side per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-level", type=int, default=0, help="oracle mesh level for the CPU legs (0 = auto)")
+    ap.add_argument("--cpu-level", type=int, default=0, help="oracle-port mesh level for the CPU legs (0 = 7)")
+    ap.add_argument("--cpu-size", type=int, default=0, help="cells per side for the compiled-reference CPU leg (0 = 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -104,8 +105,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# ---- CPU legs (the oracle, timed; never on the product path) -------------------------------------
-def cpu_reference_run(level, warmup, steps, threads):
+# ---- CPU legs (oracle/ and oracle/_ref, timed; never on the product path) -------------------------
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "minimmerflow_ref")
+
+
+def cpu_port_run(level, warmup, steps, threads):
+    """The oracle port (oracle/mmf_oracle.c) on `threads` host threads, contiguous Morton chunks."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     orc = oracle_lib.load()
@@ -114,28 +119,78 @@ def cpu_reference_run(level, warmup, steps, threads):
     return cells * 3.0 * steps / secs, secs, cells
 
 
+def cpu_reference_run(n_side, steps):
+    """The UNMODIFIED reference (oracle/_ref/minimmerflow_ref: /root/reference/src/*.cpp compiled in the
+    dev container against compat/bitpit; serial -- the reference's only parallelism is MPI, which this
+    image does not have) on the benchmark problem at n_side^3 cells for `steps` RK3 steps.  The time is
+    the reference's own "Computation time (without disk saving time)" line (src/main.cpp:371-372, 525,
+    542-544: clock() around the time loop), so mesh set-up and output are excluded like on the GPU."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reference_runner as R
+    h = 10.0 / n_side
+    # dt = 0.9*CFL*h/maxEig with maxEig ~ 2.94 for this vortex: end time placed mid-way through step `steps`
+    t_end = (steps - 0.5) * 0.9 * 0.45 * h / 2.94
+    case = dict(problem="vortex_xy", dim=3, n_cells=n_side, cfl=0.45, t_end=t_end)
+    r = R.run_case(REF_EXE, case, timeout=1800)
+    line = [ln for ln in r["output"].splitlines() if "Computation time" in ln][0]
+    secs = float(line.split(" is ")[1])
+    cells = n_side ** 3
+    return cells * 3.0 * r["steps"] / secs, secs, cells, r["steps"]
+
+
+def cpu_baseline_entry(args, cores):
+    """Bounded CPU sample of the same workload for the `cpu_baseline` object (and the reference arm)."""
+    if os.path.exists(REF_EXE):
+        n_side = args.cpu_size or 128
+        v, secs, cells, steps = cpu_reference_run(n_side, 3)
+        entry = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                 "sample": f"{steps} RK3 steps of the same problem on a {n_side}^3 mesh by the unmodified reference "
+                           f"(serial build: no MPI in the image), {secs:.1f} s of its own loop clock"}
+        timing = (secs, steps)
+    else:
+        entry = None
+    level = args.cpu_level or 7
+    pv, psecs, _ = cpu_port_run(level, 1, 2, cores)
+    port = {"value": pv, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"2 RK3 steps on a {1 << level}^3 mesh by the oracle port on {cores} threads "
+                      f"(contiguous Morton chunks, the reference's MPI decomposition), {psecs:.1f} s"}
+    if entry is None:
+        return port, None, (psecs, 2)
+    return entry, port, timing
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    level = args.cpu_level or (8 if cores >= 64 else 7)
-    # each "step" of this arm is one RK3 step of the oracle on a (2^level)^3 sample of the workload
-    steps = max(1, min(args.steps, 3))
-    warm = 1  # one untimed step: first-touch page faults of the 5 state/mesh arrays
-    value, secs, cells = cpu_reference_run(level, warm, steps, cores)
-    sample = f"{steps} RK3 steps of vortex_xy on a {1 << level}^3 uniform mesh, {cores} threads (contiguous Morton chunks)"
+    entry, port, (secs, steps) = cpu_baseline_entry(args, cores)
+    value = entry["value"]
+    S = args.size
+    px, py, pz = box_decomposition(args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
+        "steps": steps, "warmup": 0 if entry["kind"] == "reference" else 1,
+        "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3-D isentropic vortex (vortex_xy), uniform mesh, order 1, CFL 0.45; CPU sample {1 << level}^3"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(S, (S * px, S * py, S * pz), (px, py, pz)),
+        "cpu_baseline": entry,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference binary cannot be built here (bitpit absent); this is the reference-faithful CPU "
-                "restatement (oracle), which omits bitpit's per-face id lookups and VTK writes",
+        "gpu_launches": 0,
+        "note": "CPU arm: the reference's own implementation of the path on the host cores, on a bounded sample "
+                "of the workload (see cpu_baseline.sample)",
     }
+    if port is not None:
+        line["cpu_port_all_cores"] = port
     print(json.dumps(line), flush=True)
+
+
+def workload_config(S, gdims, grid):
+    return {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
+                        f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes", "path": "uniform fused stage kernels",
+            "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
 
 
 # ---- our arm --------------------------------------------------------------------------------------
@@ -217,11 +272,17 @@ def run_ours(args):
     s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)
     kms, kn = s.profile_end()
 
-    # e2e: upload + K steps + download through the C-ABI with host buffers, wall clock
+    # e2e: the call sequence a host like main.cpp makes, with HOST buffers and wall-clock time:
+    # upload the AoS state (pinned), K x mmf_step -- each returns dt and the three max eigenvalues
+    # main.cpp logs per step (src/main.cpp:399, 440, 476), i.e. one device->host read and one host
+    # sync per step -- then download the state.
     barrier()
     t0 = time.perf_counter()
     s.set_state_ptr(mmf.FIELD_U, hptr.value)
-    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)
+    t_now = 0.0
+    for _ in range(args.steps):
+        dt_k, _eig = s.step(cfl, h, t_now, t_inf)
+        t_now += dt_k
     s.get_state_ptr(mmf.FIELD_U, hptr.value)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -238,33 +299,47 @@ def run_ours(args):
         value = cells_total * 3.0 * args.steps / (ms * 1e-3)
         peak, peak_src = measured_peak()
         stage_ms = [kms[i] / kn[i] if kn[i] else None for i in (1, 2, 3)]
-        alg = sum(ALG_BYTES_PER_CELL_STAGE) * cells_local
-        achieved = alg / (sum(x for x in stage_ms if x) * 1e-3) / 1e9 if all(stage_ms) else None
+        stage_gbs = [ALG_BYTES_PER_CELL_STAGE[i] * cells_local / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] else None
+                     for i in range(3)]
+        # dominant kernel: the stage-2/3 kernel (one template, two of the three launches of a step)
+        dom_ms = (kms[2] + kms[3]) / max(kn[2] + kn[3], 1)
+        achieved = ALG_BYTES_PER_CELL_STAGE[1] * cells_local / (dom_ms * 1e-3) / 1e9 if dom_ms else None
+        step_gbs = sum(ALG_BYTES_PER_CELL_STAGE) * cells_local / (ms / args.steps * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("cells_per_launch") == cells_local:
+                traffic = tj["stage23_dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
-                                   f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
-                       "decomposition": f"{px}x{py}x{pz} boxes", "path": "uniform fused stage kernels",
-                       "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"},
+            "config": workload_config(S, gdims, (px, py, pz)),
             "clocks": clocks,
             "gpu_launches": int(launches),
             "e2e": {"value": cells_total * 3.0 * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": nbytes / args.steps, "d2h_bytes_per_step": nbytes / args.steps,
-                    "what": f"pinned host AoS upload + {args.steps} RK3 steps + download through the C-ABI"},
+                    "h2d_bytes_per_step": nbytes / args.steps, "d2h_bytes_per_step": nbytes / args.steps + 88,
+                    "what": f"pinned host AoS upload, {args.steps} x mmf_step (dt and max eigenvalues read back and the host "
+                            f"synchronised every step), download; wall clock through the C-ABI"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src,
-                         "kernel": "uniform_stage_kernel<1|2|3> (three launches per RK3 step)",
-                         "stage_ms": stage_ms, "algorithmic_bytes_per_cell": list(ALG_BYTES_PER_CELL_STAGE)},
+                         "kernel": "uniform_stage_kernel_v5r<2|3> (stages 2 and 3: two of the three launches of an RK3 step)",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE[1] * cells_local,
+                         "avg_launch_ms": dom_ms,
+                         "stage_ms": stage_ms, "stage_GBps": stage_gbs,
+                         "algorithmic_bytes_per_cell": list(ALG_BYTES_PER_CELL_STAGE),
+                         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
+                                        "what": "320 B/cell per RK3 step over the timed step time (all kernels, launch gaps included)"}},
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            level = args.cpu_level or 7
-            v, secs, cells = cpu_reference_run(level, 1, 2, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"2 RK3 steps of the same problem on a {1 << level}^3 mesh, {cores} threads, {secs:.1f} s"}
+            entry, port, _ = cpu_baseline_entry(args, os.cpu_count() or 1)
+            line["cpu_baseline"] = entry
+            if port is not None:
+                line["cpu_port_all_cores"] = port
         print(json.dumps(line), flush=True)
 
     s.close()
