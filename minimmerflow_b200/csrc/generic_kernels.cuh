@@ -134,10 +134,15 @@ __global__ void __launch_bounds__(128) generic_rhs_kernel(GenericMesh m, const d
 // dt is chosen on the device from the stage-1 max eigenvalue exactly like src/main.cpp:398-402,
 // and steps enqueued past t_max switch themselves off through `active`.
 struct StepControl {
-    double t, dt, t_max, cfl, min_h, steps, active;
+    double t, dt, t_max, cfl, min_h, steps, active; // the first seven are (re)set by the host per call
     double max_eig[3];   // per-stage max face eigenvalue (src/main.cpp:399, :440, :476)
     double max_eig_chk;  // uniform path: stage-1 face maximum re-derived by the fused kernel
+    // uniform path: max eigenvalue of the state stage 3 wrote, found right behind stage 3 from its
+    // per-tile FP32 estimates (uniform_eig_select_kernel / uniform_eig_tiles_kernel)
+    double eig_next;
+    double mismatches;   // sticky: steps whose dt eigenvalue differed from stage 1's own face maximum
 };
+constexpr int STEP_CONTROL_HOST_FIELDS = 7;
 
 // ---- RK stage loops (src/main.cpp:409-423, 445-459, 481-495) -----------------------------------
 
@@ -183,6 +188,17 @@ __global__ void choose_dt_kernel(StepControl *ctl)
     }
 }
 
+// Uniform path, start of a step: the max eigenvalue of U is either what the previous step left in
+// eig_next (have_candidate) or is computed next by the full eigenvalue pass.
+__global__ void begin_step_kernel(StepControl *ctl, int have_candidate)
+{
+    ctl->max_eig[0]  = have_candidate ? ctl->eig_next : 0.0;
+    ctl->max_eig[1]  = 0.0;
+    ctl->max_eig[2]  = 0.0;
+    ctl->max_eig_chk = 0.0;
+    ctl->eig_next    = 0.0;
+}
+
 // host-chosen dt (mmf_rk_stage keeps main.cpp's own dt logic on the host)
 __global__ void set_dt_kernel(StepControl *ctl, double dt)
 {
@@ -190,12 +206,14 @@ __global__ void set_dt_kernel(StepControl *ctl, double dt)
     ctl->active = 1.0;
 }
 
-// src/main.cpp:505-506
-__global__ void advance_time_kernel(StepControl *ctl)
+// src/main.cpp:505-506; check_eig: the uniform path compares the eigenvalue that chose dt with the
+// face maximum the fused stage-1 kernel re-derived
+__global__ void advance_time_kernel(StepControl *ctl, int check_eig)
 {
     if (ctl->active != 0.0) {
         ctl->t += ctl->dt;
         ctl->steps += 1.0;
+        if (check_eig && ctl->max_eig_chk != ctl->max_eig[0]) ctl->mismatches += 1.0;
     }
 }
 

@@ -452,7 +452,7 @@ static int step_enqueue(mmf_ctx *ctx)
     if ((rc = rk_enqueue(ctx, 3))) return rc;
     if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_U))) return rc;
     if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[1], 2))) return rc; // logged only (:436, :472)
-    advance_time_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
+    advance_time_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, 0);
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
 }
@@ -464,8 +464,10 @@ static int upload_control(mmf_ctx *ctx, double cfl, double min_h, double t, doub
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memset(h, 0, sizeof *h);
     h->t = t; h->t_max = t_max; h->cfl = cfl; h->min_h = min_h; h->steps = 0.0; h->active = 0.0;
-    MMF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ctl, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->path == MMF_PATH_UNIFORM) uniform_invalidate_eig(ctx);
+    // only the host-owned head of the block: the eigenvalue by-product of the previous step's stage 3
+    // (eig_next / eig_seed) stays valid across calls as long as nothing else touched field U
+    MMF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ctl, h, STEP_CONTROL_HOST_FIELDS * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MMF_CUDA(ctx, cudaMemsetAsync(&ctx->d_ctl->mismatches, 0, sizeof(double), ctx->stream));
     return MMF_OK;
 }
 
@@ -486,10 +488,9 @@ extern "C" int mmf_step(mmf_ctx *ctx, double cfl, double min_cell_size, double t
     if ((rc = step_enqueue(ctx))) return rc;
     ctx->state_valid[MMF_FIELD_W] = ctx->state_valid[MMF_FIELD_RHS] = true;
     if ((rc = download_control(ctx))) return rc;
-    if (ctx->path == MMF_PATH_UNIFORM && !ctx->comm && ctx->h_ctl->active != 0.0 &&
-        ctx->h_ctl->max_eig_chk != ctx->h_ctl->max_eig[0]) {
-        return fail(ctx, MMF_ERR_STATE, "mmf_step: internal check failed: cell-wise max eigenvalue %.17g != "
-                    "face-wise %.17g", ctx->h_ctl->max_eig[0], ctx->h_ctl->max_eig_chk);
+    if (ctx->h_ctl->mismatches != 0.0) {
+        return fail(ctx, MMF_ERR_STATE, "mmf_step: internal check failed: the max eigenvalue that chose dt (%.17g) is not "
+                    "the face maximum of the stage-1 residual (%.17g)", ctx->h_ctl->max_eig[0], ctx->h_ctl->max_eig_chk);
     }
     if (dt_out) *dt_out = ctx->h_ctl->dt;
     if (max_eig_out) {
@@ -525,6 +526,10 @@ extern "C" int mmf_run(mmf_ctx *ctx, double cfl, double min_cell_size, double *t
         if (bounded_time && !(ctx->h_ctl->t < t_max)) break;
     }
     ctx->state_valid[MMF_FIELD_W] = ctx->state_valid[MMF_FIELD_RHS] = true;
+    if (ctx->h_ctl->mismatches != 0.0) {
+        return fail(ctx, MMF_ERR_STATE, "mmf_run: internal check failed in %d step(s): the max eigenvalue that chose dt "
+                    "is not the face maximum of the stage-1 residual", (int) ctx->h_ctl->mismatches);
+    }
     *t = ctx->h_ctl->t;
     if (steps_out) *steps_out = (int) ctx->h_ctl->steps;
     return MMF_OK;

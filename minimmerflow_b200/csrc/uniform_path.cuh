@@ -33,13 +33,16 @@ struct UniformPath {
     double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
     int w_cur = 1;                    // which array currently holds field W
     StageShape shape[4];              // kernel form, CTA size and z chunk per stage (0 = RHS only, 1..3)
-    bool eig_valid = false;
+    float *cta_est = nullptr;         // per stage-3 tile: FP32 estimate of the max eigenvalue of what it wrote
+    int *eig_cand = nullptr;          // [0] = number of listed tiles, then their indices
+    int n_tiles3 = 0;
+    bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
 };
 
 inline int uniform_order_exact(const mmf_ctx *ctx) { return ctx->uni ? ctx->uni->order_exact : 0; }
-inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_valid = false; }
+inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_candidate = false; }
 
 inline void uniform_destroy(mmf_ctx *ctx)
 {
@@ -68,11 +71,11 @@ static int uniform_ensure_rhs(mmf_ctx *ctx)
 // ---- launch helpers -----------------------------------------------------------------------------
 
 template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
+static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    const int lz = u->shape[stage].lz;
+    const int nw = 12, lz = u->shape[stage].lz;
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
     const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -84,12 +87,29 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double 
     return MMF_OK;
 }
 
+template <typename K>
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    const int lz = u->shape[stage].lz;
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
+    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
+    MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
 template <int STAGE, int ORDER>
 static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
     const StageShape sh = u->shape[STAGE];
-    if (sh.form == '3') return launch_stage_k(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
+    if (sh.form == '3') return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
     if (sh.form == 'r') {
         if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
         if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
@@ -113,13 +133,17 @@ static int launch_stage(mmf_ctx *ctx, const double *Sin, const double *Un, doubl
 int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S); // comm.cuh
 
 // refresh the ghost shell of a padded array: physical sides from the BC, partition sides by exchange
-static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active)
+static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, double *eig_next = nullptr)
 {
     const UniformGeom &g = ctx->uni->g;
-    const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
-    dim3 grid((na + 255) / 256, nb, 6);
-    uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active);
-    MMF_LAUNCH_CHECK(ctx);
+    bool any = false; // a physical side: needs the boundary-condition pass
+    for (int s = 0; s < 6; ++s) any = any || g.bc[s] >= 0;
+    if (any) {
+        const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
+        dim3 grid((na + 255) / 256, nb, 6);
+        uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next);
+        MMF_LAUNCH_CHECK(ctx);
+    }
     if (ctx->comm) return comm_uniform_exchange_enqueue(ctx, S);
     return MMF_OK;
 }
@@ -179,6 +203,12 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             if (score > best + 1e-9) { best = score; sh.lz = lz; }
         }
         if (sh.lz <= 0) sh.lz = g.nz;
+    }
+    {
+        const StageShape &s3 = u->shape[3];
+        u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.nw - 3) / (s3.nw - 2)) * ((g.nz + s3.lz - 1) / s3.lz);
+        if ((rc = dev_alloc(ctx, &u->cta_est, (size_t) u->n_tiles3))) return rc;
+        if ((rc = dev_alloc(ctx, &u->eig_cand, (size_t) u->n_tiles3 + 1))) return rc;
     }
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMF_OK;
@@ -391,7 +421,7 @@ static int uniform_scatter_state(mmf_ctx *ctx, int field, const double *staging)
     uniform_scatter_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
         u->g, u->cell_numbering, u->cell_off, staging, S, ctx->n_cells);
     MMF_LAUNCH_CHECK(ctx);
-    if (field == MMF_FIELD_U) u->eig_valid = false;
+    if (field == MMF_FIELD_U) u->eig_candidate = false;
     if (field != MMF_FIELD_RHS) return uniform_refresh_ghosts(ctx, S, 0);
     return MMF_OK;
 }
@@ -433,15 +463,16 @@ static int uniform_rk(mmf_ctx *ctx, int stage)
     default: uniform_rk_kernel<3><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
     }
     MMF_LAUNCH_CHECK(ctx);
-    if (stage == 3) u->eig_valid = false;
+    if (stage == 3) u->eig_candidate = false;
     return uniform_refresh_ghosts(ctx, stage == 3 ? U : W, 0);
 }
 
 int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value, int count); // comm.cuh
 
 // One fused SSP-RK3 step (replaces src/main.cpp:383-506):
-//   max eigenvalue of U -> dt on the device -> three fused residual+update kernels, each followed
-//   by the ghost refresh of its output.
+//   max eigenvalue of U -> dt on the device -> three fused residual+update kernels, each followed by
+//   the ghost refresh of its output; behind stage 3 the max eigenvalue of the new U is found from the
+//   stage's per-tile estimates, so the next step starts without a pass over U.
 static int uniform_step(mmf_ctx *ctx)
 {
     UniformPath *u = ctx->uni;
@@ -450,28 +481,43 @@ static int uniform_step(mmf_ctx *ctx)
     int rc;
     double *U = u->arr[0], *Wa = u->arr[1], *Wb = u->arr[2];
 
-    MMF_CUDA(ctx, cudaMemsetAsync(&c->max_eig[0], 0, 4 * sizeof(double), ctx->stream));
-    {
+    begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, u->eig_candidate ? 1 : 0);
+    MMF_LAUNCH_CHECK(ctx);
+    if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass
         dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
         uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
         MMF_LAUNCH_CHECK(ctx);
     }
+    u->eig_candidate = false;
     if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
     choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
     MMF_LAUNCH_CHECK(ctx);
 
-    // the stage-1 kernel re-derives the same face maximum as a by-product; it is kept beside the
-    // value that chose dt and mmf_step fails loudly if the two evaluations ever disagree
+    // the stage-1 kernel re-derives the same face maximum as a by-product; advance_time_kernel
+    // compares the two and mmf_step / mmf_run fail loudly if they ever disagree
     if ((rc = launch_stage<1>(ctx, U, U, Wa, &c->max_eig_chk))) return rc;
     if ((rc = uniform_refresh_ghosts(ctx, Wa, 1))) return rc;
     if ((rc = launch_stage<2>(ctx, Wa, U, Wb, &c->max_eig[1]))) return rc;
     if ((rc = uniform_refresh_ghosts(ctx, Wb, 1))) return rc;
     if ((rc = launch_stage<3>(ctx, Wb, U, U, &c->max_eig[2]))) return rc;
-    if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
     u->w_cur = 2;
-    // the two values main.cpp only logs (:436, :472)
-    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[1], 2))) return rc;
-    advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c);
+    const StageShape &s3 = u->shape[3];
+    if (s3.form != '3') {
+        // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
+        if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
+        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.nw - 3) / (s3.nw - 2);
+        uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, u->eig_cand);
+        MMF_LAUNCH_CHECK(ctx);
+        uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 256, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.nw - 2,
+                                                                                             s3.lz, &c->eig_next);
+        MMF_LAUNCH_CHECK(ctx);
+        u->eig_candidate = true;
+    } else {
+        if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
+    }
+    // the two values main.cpp only logs (:436, :472) and the stage-1 check value, one message
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[1], 3))) return rc;
+    advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c, 1);
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
 }

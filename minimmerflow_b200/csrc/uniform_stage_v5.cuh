@@ -46,24 +46,92 @@ __device__ __forceinline__ int order_key(int coord, int axis)
     return (ORDER == NUM_LEXI) ? axis : 3 * (__ffs(coord) - 1) + axis;
 }
 
+__device__ __forceinline__ float rcp_approx_f32(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float sqrt_approx_f32(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// FP32 ESTIMATE of a cell's largest side eigenvalue max_d |u_d| + a (src/euler.cpp:59-66).  Stage 3
+// evaluates it for the state it writes and keeps the maximum per CTA; the next step's exact max
+// eigenvalue (src/main.cpp:398) is then found by re-evaluating in FP64 only the tiles whose estimate
+// comes within EIG_EST_MARGIN of the largest estimate (uniform_eig_tiles_kernel): the cell holding
+// the true maximum is necessarily in one of them, because an estimate is off by far less than the
+// margin (relative error ~1e-6: two approximate SFU operations, FP32 rounding, and the cancellation
+// in E - kinetic energy).
+constexpr float EIG_EST_MARGIN = 0.999f;
+
+__device__ __forceinline__ float eig_estimate(const double *c)
+{
+    const float r = (float) c[FID_RHO], mx = (float) c[FID_RHO_U], my = (float) c[FID_RHO_V], mz = (float) c[FID_RHO_W];
+    const float inv = rcp_approx_f32(r);
+    const float u = mx * inv, v = my * inv, w = mz * inv;
+    const float p = 0.4f * ((float) c[FID_RHO_E] - 0.5f * (mx * u + my * v + mz * w));
+    return fmaxf(fmaxf(fabsf(u), fabsf(v)), fabsf(w)) + sqrt_approx_f32(1.4f * p * inv);
+}
+
 // RK stage applied to one finished residual (src/main.cpp:409-423, 445-459, 481-495)
 template <int STAGE>
 __device__ __forceinline__ void finish_plane(const double *S, const double *AFz, const double *pU, const double *pUn,
-                                             double dt, double volume, double y_vol, double *op, long long fs, bool pred)
+                                             double dt, double volume, double y_vol, double *op, long long fs, bool pred,
+                                             float &est_max)
 {
+    double out[NF];
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
         const double rhs = S[k] - AFz[k];
-        double out;
         if (STAGE == 0) {
-            out = rhs;
+            out[k] = rhs;
         } else {
             const double dq = div_nr(dt * rhs, volume, y_vol); // dt * RHS[k] / cellVolume
-            if (STAGE == 1)      out = pU[k] + dq;
-            else if (STAGE == 2) out = 0.75 * pUn[k] + 0.25 * (pU[k] + dq);
-            else                 out = (1. / 3) * pUn[k] + (2. / 3) * (pU[k] + dq);
+            if (STAGE == 1)      out[k] = pU[k] + dq;
+            else if (STAGE == 2) out[k] = 0.75 * pUn[k] + 0.25 * (pU[k] + dq);
+            else                 out[k] = (1. / 3) * pUn[k] + (2. / 3) * (pU[k] + dq);
         }
-        if (pred) op[k * fs] = out;
+        if (pred) op[k * fs] = out[k];
+    }
+    if (STAGE == 3) {
+        const float est = eig_estimate(out);
+        est_max = fmaxf(est_max, pred ? est : 0.f); // fmaxf drops a NaN from a never-stored halo lane
+    }
+}
+
+// block-wide maxima at the end of a stage kernel: the face eigenvalue (warp shuffle, one value per
+// warp through shared memory, one integer atomic per CTA) and, for stage 3, the CTA's eigenvalue
+// estimate, stored per CTA (no atomic)
+template <int NW>
+__device__ __forceinline__ void block_maxima(double v, double *out, float est, float *cta_est, double *scratch)
+{
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+    __syncthreads(); // every warp is done with the exchange buffers
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (v < a) ? a : v;
+        est = fmaxf(est, __shfl_xor_sync(0xffffffffu, est, o));
+    }
+    if (lane == 0) { scratch[row] = v; scratch[NW + row] = (double) est; }
+    __syncthreads();
+    if (row == 0) {
+        double a = (lane < NW) ? scratch[lane] : 0.0, b = (lane < NW) ? scratch[NW + lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, a, o), y = __shfl_xor_sync(0xffffffffu, b, o);
+            a = (a < x) ? x : a;
+            b = (b < y) ? y : b;
+        }
+        if (lane == 0) {
+            atomic_max_nonneg(out, a);
+            if (cta_est) cta_est[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (float) b;
+        }
     }
 }
 
@@ -90,6 +158,7 @@ struct RowCtx {
     const double *sp, *unp;
     double *op;
     double lmx, lmy, lmz;
+    float est_max;
 
     // One plane.  On entry P is the finished state of plane kz-1 (S lacks -z_hi) and C.U holds
     // plane kz; on exit C is the finished state of plane kz and P.U holds plane kz+1.
@@ -120,7 +189,7 @@ struct RowCtx {
             const double lam = llf_area_flux(P.U, P.Fz, P.lz, C.U, C.Fz, C.lz, Ah, AFz);
             lmz = (lam < lmz) ? lmz : lam;
         }
-        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd && kz > z0);
+        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
         op += plane;
 
         // ---- plane kz+1 (<= nz, exists in the padded array) into the registers plane kz-1 just left ----
@@ -215,14 +284,15 @@ struct RowCtx {
         axis_flux<2>(q, cFz, clz);
         const double lam = llf_area_flux(P.U, P.Fz, P.lz, nU, cFz, clz, Ah, AFz);
         lmz = (lam < lmz) ? lmz : lam;
-        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd);
+        finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd, est_max);
     }
 };
 
 template <int STAGE, int ORDER, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
-                        const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz)
+                        const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
+                        float *__restrict__ cta_est)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -260,6 +330,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
     const long long fs    = g.fs;
     const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
     double lmax = 0.0;
+    float emax = 0.f;
 
     if (row == 0) {
         // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
@@ -351,6 +422,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         c.unp = Un + col + (long long) (z0 + 1) * plane;   // plane z0
         c.op  = Out + col + (long long) z0 * plane;        // plane z0-1 (the first store goes to plane z0)
         c.lmx = c.lmy = c.lmz = 0.0;
+        c.est_max = 0.f;
 
         // Two plane states in ping-pong: after body(P, C) the roles swap, so nothing is ever copied
         // from "current" to "previous" registers (the rotate form spends ~65 moves per plane on that,
@@ -386,26 +458,10 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         lmax = xf_ok ? c.lmx : 0.0;
         if (yf_ok) lmax = (c.lmy < lmax) ? lmax : c.lmy;
         if (zf_ok) lmax = (c.lmz < lmax) ? lmax : c.lmz;
+        emax = c.est_max;
     }
 
-    // ---- max eigenvalue: warp shuffle, block reduction, one atomic per CTA ----------------------
-    __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, lmax, o);
-        lmax = (lmax < other) ? other : lmax;
-    }
-    if (lane == 0) smem[row] = lmax;
-    __syncthreads();
-    if (row == 0) {
-        double v = (lane < NW) ? smem[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double other = __shfl_xor_sync(0xffffffffu, v, o);
-            v = (v < other) ? other : v;
-        }
-        if (lane == 0) atomic_max_nonneg(max_eig, v);
-    }
+    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, smem);
 }
 
 } // namespace mmf

@@ -14,7 +14,8 @@ namespace mmf {
 template <int STAGE, int ORDER, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
-                        const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz)
+                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
+                         float *__restrict__ cta_est)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -52,6 +53,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
     const long long fs    = g.fs;
     const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
     double lmax = 0.0;
+    float emax = 0.f;
 
     if (row == 0) {
         // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
@@ -126,6 +128,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         const double dt = (STAGE >= 1) ? ctl->dt : 0.0;
         const int key_x = order_key<ORDER>(g.gx0 + i, 0);
         const int key_y = order_key<ORDER>(g.gy0 + j, 1);
+        float est_max = 0.f;
 
         double *d_own = sm_d + row * 11 * 32 + lane;
         const double *d_dn = sm_d + (row - 1) * 11 * 32 + lane;
@@ -185,7 +188,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
                 const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
                 lmz = (lam < lmz) ? lmz : lam;
             }
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0);
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
             op += plane;
 
             // ---- x interface (i-1 | i): lane-1's state by warp shuffle ---------------------------------
@@ -289,31 +292,15 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             axis_flux<2>(q, cFz, clz);
             const double lam = llf_area_flux(pU, pFz, plz, nxt, cFz, clz, Ah, AFz);
             lmz = (lam < lmz) ? lmz : lam;
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd);
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
         }
         lmax = xf_ok ? lmx : 0.0;
         if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;
         if (zf_ok) lmax = (lmz < lmax) ? lmax : lmz;
+        emax = est_max;
     }
 
-    // ---- max eigenvalue: warp shuffle, block reduction, one atomic per CTA ----------------------
-    __syncthreads();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, lmax, o);
-        lmax = (lmax < other) ? other : lmax;
-    }
-    if (lane == 0) smem[row] = lmax;
-    __syncthreads();
-    if (row == 0) {
-        double v = (lane < NW) ? smem[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double other = __shfl_xor_sync(0xffffffffu, v, o);
-            v = (v < other) ? other : v;
-        }
-        if (lane == 0) atomic_max_nonneg(max_eig, v);
-    }
+    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, smem);
 }
 
 } // namespace mmf

@@ -215,3 +215,34 @@ def test_large_mesh_properties(mmf):
         s.set_state(mmf.FIELD_U, U)
         s.run(0.45, h, 0.0, 1e30, max_steps=3)
         assert bits_equal(s.get_state(mmf.FIELD_U), a)
+
+
+@pytest.mark.parametrize("problem", ["vortex_xy", "radsod"])
+def test_next_step_eigenvalue_from_stage3_estimates(mmf, oracle, problem):
+    """Behind stage 3 the next step's max eigenvalue is found by re-evaluating exactly only the tiles
+    whose FP32 estimate comes close to the largest estimate.  Two hard cases: a single hot cell whose
+    maximum collapses within a step (the maximum jumps between tiles), and the radial Sod problem whose
+    maximum sits on a plateau of identical cells (many tiles listed).  dt and the three logged
+    eigenvalues must equal the oracle's bit for bit at every step, on ragged tiles."""
+    m = oracle.problem_mesh(problem, 3, 16)
+    U = oracle.init_state(m)
+    hot = 16 * 16 * 8 + 16 * 8 + 8
+    rho = U[hot, 0]
+    U[hot, 1:4] = rho * np.array([6.0, -5.0, 4.0])
+    U[hot, 4] += 0.5 * rho * (36 + 25 + 16)
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+        s.set_state(mmf.FIELD_U, U)
+        t = 0.0
+        for _ in range(12):
+            dto, me3 = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+            dtg, meg = s.step(0.45, m["h"], t, 1e30)
+            assert dtg == dto and list(me3) == meg
+            t += dto
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+        # and through the batched loop (no host round trip between the steps)
+        s.set_state(mmf.FIELD_U, U)
+        tb, nb = s.run(0.45, m["h"], 0.0, 1e30, max_steps=12)
+        assert nb == 12 and tb == t
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
