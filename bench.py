@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--cpu-level", type=int, default=0, help="oracle-port mesh level for the CPU legs (0 = 7)")
     ap.add_argument("--cpu-size", type=int, default=0, help="cells per side for the compiled-reference CPU leg (0 = 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="exchange halos with NCCL send/recv instead of direct peer stores")
     return ap.parse_args()
 
 
@@ -189,7 +190,8 @@ def run_reference(args):
 def workload_config(S, gdims, grid):
     return {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
                         f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
-            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes", "path": "uniform fused stage kernels",
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: direct peer stores over NVLink, scalar all-reduce: NCCL)",
+            "path": "uniform fused stage kernels",
             "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
 
 
@@ -244,6 +246,11 @@ def run_ours(args):
                 return -1
             return (z * py + y) * px + x
         s.comm_set_box_neighbours([nb(-1, 0, 0), nb(1, 0, 0), nb(0, -1, 0), nb(0, 1, 0), nb(0, 0, -1), nb(0, 0, 1)])
+        if not args.nccl_halo:
+            # halo exchange by direct peer stores over NVLink: gather every rank's CUDA IPC handles
+            blobs = [None] * world
+            dist.all_gather_object(blobs, s.comm_ipc_export())
+            s.comm_ipc_import(blobs)
 
     def barrier():
         if dist is not None:

@@ -103,6 +103,8 @@ SIGNATURES = {
     "mmf_comm_set_ghost_lists": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mmf_comm_set_box_neighbours": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "mmf_comm_ipc_export": (C.c_int, [_P, _P]),
+    "mmf_comm_ipc_import": (C.c_int, [_P, _P]),
     "mmf_exchange": (C.c_int, [_P, C.c_int]),
     "mmf_allreduce_max": (C.c_int, [_P, _D]),
     "mmf_timer_start": (C.c_int, [_P]),

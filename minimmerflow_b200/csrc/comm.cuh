@@ -105,9 +105,12 @@ static int comm_init(mmf_ctx *ctx, int rank, int n_ranks, const void *unique_id)
     return MMF_OK;
 }
 
+static void comm_ipc_close(mmf_ctx *ctx);
+
 static void comm_destroy(mmf_ctx *ctx)
 {
     if (!ctx->comm) return;
+    comm_ipc_close(ctx);
     if (ctx->comm->comm) nccl_api().CommDestroy(ctx->comm->comm);
     delete ctx->comm;
     ctx->comm = nullptr;
@@ -248,10 +251,160 @@ static int comm_set_box_neighbours(mmf_ctx *ctx, const int32_t ranks[6])
     return MMF_OK;
 }
 
+// ---- uniform path: halo exchange by direct peer stores (NVLink P2P through CUDA IPC) -----------
+// One kernel copies every partition-side boundary layer of S straight into the ghost layer of the
+// neighbour's copy of the same array (no pack buffer, no NCCL rendezvous, no unpack); its last block
+// then raises this rank's arrival counter in every neighbour.  The consumer is a one-warp kernel in
+// front of the next stage that waits for the counters of all its neighbours.
+struct PushArgs {
+    double *dst[6];               // neighbour's array (same field layout, same box dimensions)
+    unsigned long long *flag[6];  // neighbour's arrival counter for the side this rank sits on
+};
+
+__global__ void __launch_bounds__(256) uniform_push_kernel(const UniformGeom g, const double *__restrict__ S, const PushArgs args,
+                                                           unsigned int *__restrict__ done, unsigned long long seq)
+{
+    const int side = blockIdx.z;
+    if (args.dst[side]) {
+        const int axis = side >> 1;
+        const bool hi = side & 1;
+        const int na = (axis == 0) ? g.ny : g.nx, nb = (axis == 2) ? g.ny : g.nz;
+        const int n_ax = (axis == 0) ? g.nx : (axis == 1) ? g.ny : g.nz;
+        const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+        if (a < na && b < nb) {
+            const int own = hi ? n_ax - 1 : 0, ghost = hi ? -1 : n_ax; // my layer -> the neighbour's ghost layer
+            long long so, go;
+            if (axis == 0)      { so = uoff(g, own, a, b); go = uoff(g, ghost, a, b); }
+            else if (axis == 1) { so = uoff(g, a, own, b); go = uoff(g, a, ghost, b); }
+            else                { so = uoff(g, a, b, own); go = uoff(g, a, b, ghost); }
+            double *d = args.dst[side];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) d[f * g.fs + go] = S[f * g.fs + so];
+        }
+    }
+    // last block out raises the arrival counters: every block's stores are fenced at system scope
+    // before it counts itself done, so they are performed before the counters move
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        last = (atomicAdd(done, 1u) == total - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 6 && args.flag[threadIdx.x]) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(args.flag[threadIdx.x]) = seq;
+        if (threadIdx.x == 0) *done = 0;
+    } else if (last && threadIdx.x == 0) {
+        *done = 0;
+    }
+}
+
+__global__ void uniform_wait_kernel(const unsigned long long *flags, unsigned int side_mask, unsigned long long seq)
+{
+    const int s = threadIdx.x;
+    if (s < 6 && ((side_mask >> s) & 1u)) {
+        const volatile unsigned long long *f = flags + s;
+        while (*f < seq) { }
+    }
+    __threadfence_system();
+}
+
+constexpr size_t IPC_BLOB_BYTES = 4 * sizeof(cudaIpcMemHandle_t);
+
+static int comm_ipc_export(mmf_ctx *ctx, void *out)
+{
+    if (ctx->path != MMF_PATH_UNIFORM) return fail(ctx, MMF_ERR_STATE, "mmf_comm_ipc_export: uniform path only");
+    UniformPath *u = ctx->uni;
+    int rc;
+    if (!u->flags) {
+        if ((rc = dev_alloc(ctx, &u->flags, 8))) return rc;
+        if ((rc = dev_alloc(ctx, &u->push_count, 1))) return rc;
+        MMF_CUDA(ctx, cudaMemset(u->flags, 0, 8 * sizeof(unsigned long long)));
+        MMF_CUDA(ctx, cudaMemset(u->push_count, 0, sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t *h = static_cast<cudaIpcMemHandle_t *>(out);
+    for (int a = 0; a < 3; ++a) MMF_CUDA(ctx, cudaIpcGetMemHandle(&h[a], u->arr[a]));
+    MMF_CUDA(ctx, cudaIpcGetMemHandle(&h[3], u->flags));
+    return MMF_OK;
+}
+
+static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
+{
+    Comm *c = ctx->comm;
+    if (!c) return fail(ctx, MMF_ERR_STATE, "mmf_comm_ipc_import: call mmf_comm_init first");
+    if (ctx->path != MMF_PATH_UNIFORM) return fail(ctx, MMF_ERR_STATE, "mmf_comm_ipc_import: uniform path only");
+    UniformPath *u = ctx->uni;
+    if (!u->flags) return fail(ctx, MMF_ERR_STATE, "mmf_comm_ipc_import: call mmf_comm_ipc_export first");
+    const char *blob = static_cast<const char *>(all_ranks);
+    for (int s = 0; s < 6; ++s) {
+        const int r = u->nbr_rank[s];
+        if (r < 0) continue;
+        if (r == c->rank) return fail(ctx, MMF_ERR_INVALID, "mmf_comm_ipc_import: a box cannot neighbour itself");
+        const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(blob + (size_t) r * IPC_BLOB_BYTES);
+        // the same neighbour may sit on several sides only in degenerate grids; open per side anyway
+        for (int a = 0; a < 4; ++a) {
+            void *p = nullptr;
+            bool reused = false;
+            for (int s2 = 0; s2 < s && !reused; ++s2) {
+                if (u->nbr_rank[s2] == r) { p = u->ipc_opened[s2][a]; reused = true; }
+            }
+            if (!reused) {
+                cudaIpcMemHandle_t hh;
+                memcpy(&hh, &h[a], sizeof hh);
+                MMF_CUDA(ctx, cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
+                u->ipc_opened[s][a] = p;
+            }
+            if (a < 3) u->peer_arr[s][a] = static_cast<double *>(p);
+            else       u->peer_flags[s] = static_cast<unsigned long long *>(p) + (s ^ 1); // I sit on its opposite side
+        }
+    }
+    u->p2p = true;
+    return MMF_OK;
+}
+
+static void comm_ipc_close(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    if (!u) return;
+    for (int s = 0; s < 6; ++s)
+        for (int a = 0; a < 4; ++a)
+            if (u->ipc_opened[s][a]) { cudaIpcCloseMemHandle(u->ipc_opened[s][a]); u->ipc_opened[s][a] = nullptr; }
+    u->p2p = false;
+}
+
+static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    int a = -1;
+    for (int q = 0; q < 3; ++q) if (S == u->arr[q]) a = q;
+    if (a < 0) return fail(ctx, MMF_ERR_STATE, "peer exchange is defined for the U / W arrays only");
+    PushArgs args{};
+    unsigned int mask = 0;
+    for (int s = 0; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        args.dst[s] = u->peer_arr[s][a];
+        args.flag[s] = u->peer_flags[s];
+        mask |= 1u << s;
+    }
+    if (!mask) return MMF_OK;
+    const unsigned long long seq = ++u->xchg_seq;
+    const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
+    dim3 grid((na + 255) / 256, nb, 6);
+    uniform_push_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, args, u->push_count, seq);
+    MMF_LAUNCH_CHECK(ctx);
+    uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
 int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S)
 {
     Comm *c = ctx->comm;
     UniformPath *u = ctx->uni;
+    if (u->p2p) return comm_uniform_push_enqueue(ctx, S);
     const UniformGeom &g = u->g;
     bool any = false;
     for (int s = 0; s < 6; ++s) {

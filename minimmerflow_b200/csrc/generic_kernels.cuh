@@ -140,6 +140,7 @@ struct StepControl {
     // uniform path: max eigenvalue of the state stage 3 wrote, found right behind stage 3 from its
     // per-tile FP32 estimates (uniform_eig_select_kernel / uniform_eig_tiles_kernel)
     double eig_next;
+    double est_max;      // largest FP32 eigenvalue estimate over the tiles (all ranks after the all-reduce)
     double mismatches;   // sticky: steps whose dt eigenvalue differed from stage 1's own face maximum
 };
 constexpr int STEP_CONTROL_HOST_FIELDS = 7;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -169,6 +170,7 @@ static int create_common(mmf_ctx *ctx, int device)
                     device, ctx->prop.major, ctx->prop.minor);
     }
     ctx->device = device;
+    ctx->tracing = getenv("MMF_TRACE") && atoi(getenv("MMF_TRACE")) != 0;
     MMF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     MMF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     MMF_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
@@ -235,6 +237,7 @@ extern "C" int mmf_destroy(mmf_ctx *ctx)
     if (!ctx) return MMF_OK;
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    trace_report(ctx);
     comm_destroy(ctx);
     uniform_destroy(ctx);
     for (void *p : ctx->owned) cudaFree(p);
@@ -565,6 +568,22 @@ extern "C" int mmf_comm_set_box_neighbours(mmf_ctx *ctx, const int32_t neighbour
     return comm_set_box_neighbours(ctx, neighbour_ranks);
 }
 
+extern "C" int mmf_comm_ipc_export(mmf_ctx *ctx, void *blob_out)
+{
+    int rc = check_field(ctx, MMF_FIELD_U, "mmf_comm_ipc_export");
+    if (rc) return rc;
+    if (!blob_out) return fail(ctx, MMF_ERR_INVALID, "mmf_comm_ipc_export: null buffer");
+    return comm_ipc_export(ctx, blob_out);
+}
+
+extern "C" int mmf_comm_ipc_import(mmf_ctx *ctx, const void *all_ranks_blobs)
+{
+    int rc = check_field(ctx, MMF_FIELD_U, "mmf_comm_ipc_import");
+    if (rc) return rc;
+    if (!all_ranks_blobs) return fail(ctx, MMF_ERR_INVALID, "mmf_comm_ipc_import: null buffer");
+    return comm_ipc_import(ctx, all_ranks_blobs);
+}
+
 extern "C" int mmf_exchange(mmf_ctx *ctx, int field)
 {
     int rc = check_field(ctx, field, "mmf_exchange");
@@ -599,6 +618,8 @@ extern "C" int mmf_timer_start(mmf_ctx *ctx)
 {
     if (!ctx) return fail(nullptr, MMF_ERR_INVALID, "mmf_timer_start: null handle");
     MMF_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (auto &t : ctx->trace) cudaEventDestroy(t.ev); // MMF_TRACE covers the timed region only
+    ctx->trace.clear();
     MMF_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     return MMF_OK;
 }
@@ -610,6 +631,8 @@ extern "C" int mmf_timer_stop(mmf_ctx *ctx, float *milliseconds)
     MMF_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     MMF_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
     MMF_CUDA(ctx, cudaEventElapsedTime(milliseconds, ctx->ev_start, ctx->ev_stop));
+    trace_report(ctx);
+    ctx->tracing = false; // one report per process
     return MMF_OK;
 }
 

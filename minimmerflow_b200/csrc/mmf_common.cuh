@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -49,6 +50,11 @@ struct mmf_ctx {
 
     mmf::UniformPath *uni = nullptr;
     mmf::Comm *comm = nullptr;
+
+    // MMF_TRACE=1: events between the phases of a uniform step, summarised on stderr at destroy
+    bool tracing = false;
+    struct TracePoint { const char *label; cudaEvent_t ev; };
+    std::vector<TracePoint> trace;
 
     // optional per-launch timing of the residual kernels (CUDA events on the launching stream)
     bool profiling = false;
@@ -125,6 +131,37 @@ struct ScopedLaunchTimer {
     }
     ~ScopedLaunchTimer() { if (e1) cudaEventRecord(e1, ctx->stream); }
 };
+
+inline void trace_point(mmf_ctx *ctx, const char *label)
+{
+    if (!ctx->tracing || ctx->trace.size() > 20000) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    ctx->trace.push_back({ label, e });
+}
+
+inline void trace_report(mmf_ctx *ctx)
+{
+    if (ctx->trace.size() < 2) return;
+    cudaStreamSynchronize(ctx->stream);
+    struct Acc { const char *label; double ms; int n; };
+    std::vector<Acc> acc;
+    // each interval is attributed to the label at its END
+    const size_t first = 0;
+    for (size_t i = std::max<size_t>(first, 1); i < ctx->trace.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->trace[i - 1].ev, ctx->trace[i].ev) != cudaSuccess) continue;
+        bool found = false;
+        for (auto &a : acc) if (a.label == ctx->trace[i].label) { a.ms += ms; a.n++; found = true; }
+        if (!found) acc.push_back({ ctx->trace[i].label, ms, 1 });
+    }
+    fprintf(stderr, "[mmf trace, device %d] average time up to each point (ms):", ctx->device);
+    for (auto &a : acc) fprintf(stderr, "  %s=%.4f(x%d)", a.label, a.ms / a.n, a.n);
+    fprintf(stderr, "\n");
+    for (auto &t : ctx->trace) cudaEventDestroy(t.ev);
+    ctx->trace.clear();
+}
 
 inline unsigned grid_for(int64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 

@@ -39,6 +39,15 @@ struct UniformPath {
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
+    // direct peer stores over NVLink (comm.cuh): the neighbours' state arrays and arrival flags,
+    // mapped through CUDA IPC
+    bool p2p = false;
+    double *peer_arr[6][3] = {};
+    unsigned long long *flags = nullptr;            // [6] arrival counters, written by the neighbours
+    unsigned long long *peer_flags[6] = {};
+    unsigned int *push_count = nullptr;             // blocks of the running push kernel that are done
+    unsigned long long xchg_seq = 0;
+    void *ipc_opened[6][4] = {};
 };
 
 inline int uniform_order_exact(const mmf_ctx *ctx) { return ctx->uni ? ctx->uni->order_exact : 0; }
@@ -481,44 +490,58 @@ static int uniform_step(mmf_ctx *ctx)
     int rc;
     double *U = u->arr[0], *Wa = u->arr[1], *Wb = u->arr[2];
 
+    trace_point(ctx, "gap");
     begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, u->eig_candidate ? 1 : 0);
     MMF_LAUNCH_CHECK(ctx);
-    if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass
+    if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass (+ all-reduce)
         dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
         uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
         MMF_LAUNCH_CHECK(ctx);
-    }
+        if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
+    } // else: eig_next was reduced over the ranks at the end of the previous step
     u->eig_candidate = false;
-    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
     choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
     MMF_LAUNCH_CHECK(ctx);
+    trace_point(ctx, "begin+dt");
 
     // the stage-1 kernel re-derives the same face maximum as a by-product; advance_time_kernel
     // compares the two and mmf_step / mmf_run fail loudly if they ever disagree
     if ((rc = launch_stage<1>(ctx, U, U, Wa, &c->max_eig_chk))) return rc;
+    trace_point(ctx, "stage1");
     if ((rc = uniform_refresh_ghosts(ctx, Wa, 1))) return rc;
+    trace_point(ctx, "halo1");
     if ((rc = launch_stage<2>(ctx, Wa, U, Wb, &c->max_eig[1]))) return rc;
+    trace_point(ctx, "stage2");
     if ((rc = uniform_refresh_ghosts(ctx, Wb, 1))) return rc;
+    trace_point(ctx, "halo2");
     if ((rc = launch_stage<3>(ctx, Wb, U, U, &c->max_eig[2]))) return rc;
+    trace_point(ctx, "stage3");
     u->w_cur = 2;
     const StageShape &s3 = u->shape[3];
     if (s3.form != '3') {
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
         const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.nw - 3) / (s3.nw - 2);
-        uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, u->eig_cand);
+        uniform_eig_estmax_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max);
         MMF_LAUNCH_CHECK(ctx);
-        uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 256, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.nw - 2,
+        if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->est_max, 1))) return rc;
+        uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max, u->eig_cand);
+        MMF_LAUNCH_CHECK(ctx);
+        uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 320, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.nw - 2,
                                                                                              s3.lz, &c->eig_next);
         MMF_LAUNCH_CHECK(ctx);
         u->eig_candidate = true;
+        trace_point(ctx, "halo3+eig");
     } else {
         if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
     }
-    // the two values main.cpp only logs (:436, :472) and the stage-1 check value, one message
-    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[1], 3))) return rc;
+    // one message per step: the two values main.cpp only logs (:436, :472), the stage-1 check value
+    // and the next step's max eigenvalue (max_eig[1], max_eig[2], max_eig_chk, eig_next are contiguous)
+    if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[1], 4))) return rc;
+    trace_point(ctx, "allreduce");
     advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c, 1);
     MMF_LAUNCH_CHECK(ctx);
+    trace_point(ctx, "advance");
     return MMF_OK;
 }
 

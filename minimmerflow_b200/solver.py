@@ -221,6 +221,19 @@ class EulerSolver:
         self._ck(self._lib.mmf_comm_set_ghost_lists(self._h, n, _ptr(ranks, C.c_int32), _ptr(so, C.c_int64),
                                                     _ptr(si, C.c_int64), _ptr(ro, C.c_int64), _ptr(ri, C.c_int64)))
 
+    IPC_BLOB_BYTES = 256
+
+    def comm_ipc_export(self):
+        buf = (C.c_char * self.IPC_BLOB_BYTES)()
+        self._ck(self._lib.mmf_comm_ipc_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_ipc_import(self, blobs):
+        """blobs: the exported blobs of ALL ranks, in rank order."""
+        data = b"".join(blobs)
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        self._ck(self._lib.mmf_comm_ipc_import(self._h, buf))
+
     def exchange(self, field):
         self._ck(self._lib.mmf_exchange(self._h, field))
 

@@ -32,6 +32,21 @@ def _share_unique_id(mmf, rank, path):
     raise RuntimeError("no NCCL unique id")
 
 
+def _share_ipc(s, rank, world, path):
+    blob = s.comm_ipc_export()
+    with open(f"{path}_{rank}.tmp", "wb") as f:
+        f.write(blob)
+    os.replace(f"{path}_{rank}.tmp", f"{path}_{rank}")
+    blobs = []
+    for r in range(world):
+        for _ in range(600):
+            if os.path.exists(f"{path}_{r}"):
+                break
+            time.sleep(0.05)
+        blobs.append(open(f"{path}_{r}", "rb").read())
+    s.comm_ipc_import(blobs)
+
+
 def _worker(rank, world, mode, problem, n, steps, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -43,7 +58,7 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
     U = orc.init_state(m)
     uid = _share_unique_id(mmf, rank, os.path.join(out_dir, f"uid_{mode}"))
     h = m["h"]
-    if mode == "uniform":
+    if mode.startswith("uniform"):
         grid = box_decomposition(world)
         dims = (n // grid[0], n // grid[1], n // grid[2])
         offset, nbrs = box_of_rank(rank, grid, dims)
@@ -57,6 +72,8 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
                                     interface_numbering=mmf.NUMBERING_MORTON, global_dims=(n, n, n), box_offset=offset)
         s.comm_init(rank, world, uid)
         s.comm_set_box_neighbours(nbrs)
+        if mode == "uniform_p2p":
+            _share_ipc(s, rank, world, os.path.join(out_dir, f"ipc_{mode}"))
         s.set_state(mmf.FIELD_U, U[gids])
         n_int = len(gids)
     else:
@@ -81,7 +98,8 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
     s.close()
 
 
-@pytest.mark.parametrize("mode,problem", [("uniform", "vortex_xy"), ("uniform", "radsod"), ("generic", "vortex_xy")])
+@pytest.mark.parametrize("mode,problem", [("uniform_p2p", "vortex_xy"), ("uniform_p2p", "radsod"), ("uniform", "vortex_xy"),
+                                          ("uniform", "radsod"), ("generic", "vortex_xy")])
 def test_two_gpu_run_equals_serial_oracle(mmf, oracle, tmp_path, mode, problem):
     if mmf.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
