@@ -37,6 +37,7 @@ struct UniformPath {
     int *eig_cand = nullptr;          // [0] = number of listed tiles, then their indices
     int n_tiles3 = 0;
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
+    bool clamp_ff = true;             // no stage runs the v3 form: free-flow ghosts are never read
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
     // direct peer stores over NVLink (comm.cuh): the neighbours' state arrays and arrival flags,
@@ -79,6 +80,21 @@ static int uniform_ensure_rhs(mmf_ctx *ctx)
 
 // ---- launch helpers -----------------------------------------------------------------------------
 
+// free-flow sides: the v5 stage kernels re-read the boundary cell instead of a ghost cell
+static LoadClamp uniform_load_clamp(const UniformPath *u)
+{
+    const UniformGeom &g = u->g;
+    const bool on = u->clamp_ff;
+    LoadClamp lc;
+    lc.ilo = (on && g.bc[0] == BC_FREE_FLOW) ? 0 : -1;
+    lc.ihi = (on && g.bc[1] == BC_FREE_FLOW) ? g.nx - 1 : g.nx;
+    lc.jlo = (on && g.bc[2] == BC_FREE_FLOW) ? 0 : -1;
+    lc.jhi = (on && g.bc[3] == BC_FREE_FLOW) ? g.ny - 1 : g.ny;
+    lc.klo = (on && g.bc[4] == BC_FREE_FLOW) ? 0 : -1;
+    lc.khi = (on && g.bc[5] == BC_FREE_FLOW) ? g.nz - 1 : g.nz;
+    return lc;
+}
+
 template <typename K>
 static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
 {
@@ -107,7 +123,8 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double 
     MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     {
         ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr);
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
+                                                   uniform_load_clamp(u));
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -145,12 +162,14 @@ int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S); // comm.cuh
 static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, double *eig_next = nullptr)
 {
     const UniformGeom &g = ctx->uni->g;
-    bool any = false; // a physical side: needs the boundary-condition pass
-    for (int s = 0; s < 6; ++s) any = any || g.bc[s] >= 0;
+    // in a fused step (check_active) free-flow sides need no ghosts: the stage kernels clamp their loads
+    const int skip_ff = (check_active && ctx->uni->clamp_ff) ? 1 : 0;
+    bool any = false; // a physical side that needs the boundary-condition pass
+    for (int s = 0; s < 6; ++s) any = any || (g.bc[s] >= 0 && !(skip_ff && g.bc[s] == BC_FREE_FLOW));
     if (any) {
         const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
         dim3 grid((na + 255) / 256, nb, 6);
-        uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next);
+        uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next, skip_ff);
         MMF_LAUNCH_CHECK(ctx);
     }
     if (ctx->comm) return comm_uniform_exchange_enqueue(ctx, S);
@@ -197,6 +216,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
     // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
     // derives for its first z interface; chunks stay between 16 and 96 planes.
+    u->clamp_ff = true;
+    for (int st = 0; st < 4; ++st) u->clamp_ff = u->clamp_ff && u->shape[st].form != '3';
     const char *env_lz = getenv("MMF_STAGE_LZ");
     for (int st = 0; st < 4; ++st) {
         StageShape &sh = u->shape[st];

@@ -148,7 +148,7 @@ struct PlaneState {
 template <int STAGE, int ORDER>
 struct RowCtx {
     bool upd;
-    int lane, key_x, key_y, gz0;
+    int lane, key_x, key_y, gz0, khi;
     double dt, Ah, volume;
     DivConsts dc;
     long long fs, plane;
@@ -192,8 +192,9 @@ struct RowCtx {
         finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
         op += plane;
 
-        // ---- plane kz+1 (<= nz, exists in the padded array) into the registers plane kz-1 just left ----
-        sp += plane;
+        // ---- plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side) into the registers
+        //      plane kz-1 just left ---------------------------------------------------------------
+        if (kz + 1 <= khi) sp += plane;
 #pragma unroll
         for (int k = 0; k < NF; ++k) P.U[k] = sp[k * fs];
 
@@ -292,7 +293,7 @@ template <int STAGE, int ORDER, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                        float *__restrict__ cta_est)
+                        float *__restrict__ cta_est, const LoadClamp lc)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -315,8 +316,8 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
     const int j  = blockIdx.y * (NW - 2) - 1 + row;
     const int z0 = blockIdx.z * lz;
     const int z1 = min(z0 + lz, g.nz);
-    const int ic = min(max(i, -1), g.nx);
-    const int jc = min(max(j, -1), g.ny);
+    const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
+    const int jc = min(max(j, lc.jlo), lc.jhi);
     const bool in_x = (i >= 0 && i < g.nx);
     const bool in_y = (j >= 0 && j < g.ny);
 
@@ -408,6 +409,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         c.key_x = order_key<ORDER>(g.gx0 + i, 0);
         c.key_y = order_key<ORDER>(g.gy0 + j, 1);
         c.gz0   = g.gz0;
+        c.khi   = lc.khi;
         c.fs    = fs;
         c.plane = plane;
         c.d_own = sm_d + row * 11 * 32 + lane;
@@ -418,7 +420,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         c.barD_dn  = &barD[row - 1];
         c.barF_own = &barF[row];
         c.barF_up  = &barF[row + 1];
-        c.sp  = Sin + col + (long long) z0 * plane;        // plane z0-1
+        c.sp  = Sin + col + (long long) (max(z0 - 1, lc.klo) + 1) * plane; // plane z0-1 (clamped)
         c.unp = Un + col + (long long) (z0 + 1) * plane;   // plane z0
         c.op  = Out + col + (long long) z0 * plane;        // plane z0-1 (the first store goes to plane z0)
         c.lmx = c.lmy = c.lmz = 0.0;
@@ -432,7 +434,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         {
 #pragma unroll
             for (int k = 0; k < NF; ++k) A.U[k] = c.sp[k * fs];
-            c.sp += plane;
+            c.sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
 #pragma unroll
             for (int k = 0; k < NF; ++k) B.U[k] = c.sp[k * fs];
             CellPrim q;

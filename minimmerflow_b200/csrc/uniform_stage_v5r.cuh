@@ -15,7 +15,7 @@ template <int STAGE, int ORDER, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                          const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                         float *__restrict__ cta_est)
+                         float *__restrict__ cta_est, const LoadClamp lc)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -38,8 +38,8 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
     const int j  = blockIdx.y * (NW - 2) - 1 + row;
     const int z0 = blockIdx.z * lz;
     const int z1 = min(z0 + lz, g.nz);
-    const int ic = min(max(i, -1), g.nx);
-    const int jc = min(max(j, -1), g.ny);
+    const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
+    const int jc = min(max(j, lc.jlo), lc.jhi);
     const bool in_x = (i >= 0 && i < g.nx);
     const bool in_y = (j >= 0 && j < g.ny);
 
@@ -135,7 +135,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         double *f_own = sm_f + row * NF * 32 + lane;
         const double *f_up = sm_f + (row + 1) * NF * 32 + lane;
 
-        const double *sp  = Sin + col + (long long) z0 * plane; // plane z0-1
+        const double *sp  = Sin + col + (long long) (max(z0 - 1, lc.klo) + 1) * plane; // plane z0-1 (clamped)
         const double *unp = Un + col + (long long) (z0 + 1) * plane; // plane z0
         double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
 
@@ -145,7 +145,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         {
 #pragma unroll
             for (int k = 0; k < NF; ++k) pU[k] = sp[k * fs];
-            sp += plane;
+            sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
 #pragma unroll
             for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
             CellPrim q;
@@ -160,7 +160,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane; // plane kz+1 <= nz exists in the padded array
+            if (kz + 1 <= lc.khi) sp += plane; // plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side)
 #pragma unroll
             for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
             double cUn[NF];
