@@ -139,10 +139,12 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     if (sh.form == 'r') {
         if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
         if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
+        if (sh.nw == 10) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 10>, STAGE, 10, Sin, Un, Out, d_max);
         return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
     }
     if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
     if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
+    if (sh.nw == 10) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 10>, STAGE, 10, Sin, Un, Out, d_max);
     return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
 }
 
@@ -207,7 +209,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 10 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages

@@ -135,6 +135,14 @@ __device__ __forceinline__ void block_maxima(double v, double *out, float est, f
     }
 }
 
+// Registers per thread for a CTA of NW warps that owns a whole SM.  The register file is handed out
+// in units of four warps, so 13..16 warps all get 128 registers per thread (a 14-warp CTA at 144
+// fails to launch) and 9..12 warps get 168; only the 4-warp steps are worth instantiating.
+__host__ __device__ constexpr int stage_regs(int nw)
+{
+    return (65536 / ((nw + 3) / 4 * 4 * 32) / 8 * 8 > 255) ? 248 : 65536 / ((nw + 3) / 4 * 4 * 32) / 8 * 8;
+}
+
 // state of one plane of one cell as it travels through two iterations
 struct PlaneState {
     double U[NF];   // residual input of the plane
@@ -290,7 +298,7 @@ struct RowCtx {
 };
 
 template <int STAGE, int ORDER, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
                         float *__restrict__ cta_est, const LoadClamp lc)

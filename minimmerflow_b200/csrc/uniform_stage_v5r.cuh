@@ -12,7 +12,7 @@
 namespace mmf {
 
 template <int STAGE, int ORDER, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                          const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
                          float *__restrict__ cta_est, const LoadClamp lc)

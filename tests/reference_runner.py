@@ -4,6 +4,9 @@
                                    (CPU); built in the dev container by ``make -C oracle ref``.
 * ``minimmerflow_b200_dropin``  -- the same unmodified main.cpp & co. linked with the GPU adapters
                                    (minimmerflow_b200/adapters/solver_b200.cpp) and libmmf_b200.so.
+* ``minimmerflow_b200_resident`` -- the reference's set-up / output units unchanged, with
+                                   minimmerflow_b200/adapters/driver_b200.cpp as main(): the time loop
+                                   is a stream of mmf_step calls, the state stays in HBM.
 
 Both read ./settings.xml and print the reference's " Final error:  %.12e" line; this module writes
 the settings file from a case description, runs the binary in a scratch directory and parses the
@@ -19,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_EXE = os.path.join(REF_DIR, "minimmerflow_ref")
 DROPIN_EXE = os.path.join(REF_DIR, "minimmerflow_b200_dropin")
+RESIDENT_EXE = os.path.join(REF_DIR, "minimmerflow_b200_resident")
 
 
 def settings_xml(case):
