@@ -122,7 +122,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmmf_b200.so")
+    # MMF_LIB_PATH: development override (e.g. a build with different compiler flags)
+    return os.environ.get("MMF_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmmf_b200.so")
 
 
 def load_library():

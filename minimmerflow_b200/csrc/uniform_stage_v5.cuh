@@ -200,12 +200,6 @@ struct RowCtx {
         finish_plane<STAGE>(P.S, AFz, P.U, P.Un, dt, volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
         op += plane;
 
-        // ---- plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side) into the registers
-        //      plane kz-1 just left ---------------------------------------------------------------
-        if (kz + 1 <= khi) sp += plane;
-#pragma unroll
-        for (int k = 0; k < NF; ++k) P.U[k] = sp[k * fs];
-
         // ---- x interface (i-1 | i): lane-1's state by warp shuffle -------------------------------------
         double AFx[NF];
         {
@@ -221,6 +215,14 @@ struct RowCtx {
         // ---- y interface (j-1 | j): row-1's record through shared memory ------------------------------
         double AFy[NF];
         mbar_wait(barD_dn, par);
+        // ---- plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side) into the registers
+        //      plane kz-1 left in finish_plane.  Issued BEHIND the acquire on purpose: ptxas cannot
+        //      hoist the loads above it into the live range of the old values, which made it park the
+        //      results in other registers and copy them right behind the loads (a DRAM round trip
+        //      exposed in every plane, 15 % of all stall samples in profiles/r01b).
+        if (kz + 1 <= khi) sp += plane;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) P.U[k] = sp[k * fs];
         {
             double lU[NF], lF[NF];
 #pragma unroll
