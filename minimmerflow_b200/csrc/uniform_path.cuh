@@ -113,13 +113,15 @@ static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, c
 }
 
 template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max,
+                          int smem_doubles_per_lane = 16)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
     const int lz = u->shape[stage].lz;
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
-    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
+    // record (11) + flux (5) doubles per lane and row, two mbarriers per row
+    const size_t smem = (size_t) nw * smem_doubles_per_lane * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     {
         ScopedLaunchTimer timer(ctx, stage);
