@@ -144,7 +144,7 @@ def cpu_baseline_entry(args, cores):
     """Bounded CPU sample of the same workload for the `cpu_baseline` object (and the reference arm)."""
     if os.path.exists(REF_EXE):
         n_side = args.cpu_size or 128
-        v, secs, cells, steps = cpu_reference_run(n_side, 3)
+        v, secs, cells, steps = cpu_reference_run(n_side, 8)
         entry = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                  "sample": f"{steps} RK3 steps of the same problem on a {n_side}^3 mesh by the unmodified reference "
                            f"(serial build: no MPI in the image), {secs:.1f} s of its own loop clock"}
@@ -152,12 +152,12 @@ def cpu_baseline_entry(args, cores):
     else:
         entry = None
     level = args.cpu_level or 7
-    pv, psecs, _ = cpu_port_run(level, 1, 2, cores)
+    pv, psecs, _ = cpu_port_run(level, 1, 4, cores)
     port = {"value": pv, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"2 RK3 steps on a {1 << level}^3 mesh by the oracle port on {cores} threads "
+            "sample": f"4 RK3 steps on a {1 << level}^3 mesh by the oracle port on {cores} threads "
                       f"(contiguous Morton chunks, the reference's MPI decomposition), {psecs:.1f} s"}
     if entry is None:
-        return port, None, (psecs, 2)
+        return port, None, (psecs, 4)
     return entry, port, timing
 
 
