@@ -259,13 +259,14 @@ static int comm_set_box_neighbours(mmf_ctx *ctx, const int32_t ranks[6])
 struct PushArgs {
     double *dst[6];               // neighbour's array (same field layout, same box dimensions)
     unsigned long long *flag[6];  // neighbour's arrival counter for the side this rank sits on
+    int side_of_slot[6];          // blockIdx.z -> side: only sides that have a neighbour are launched
 };
 
 __global__ void __launch_bounds__(256) uniform_push_kernel(const UniformGeom g, const double *__restrict__ S, const PushArgs args,
                                                            unsigned int *__restrict__ done, unsigned long long seq)
 {
-    const int side = blockIdx.z;
-    if (args.dst[side]) {
+    const int side = args.side_of_slot[blockIdx.z];
+    {
         const int axis = side >> 1;
         const bool hi = side & 1;
         const int na = (axis == 0) ? g.ny : g.nx, nb = (axis == 2) ? g.ny : g.nz;
@@ -361,7 +362,7 @@ static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
         }
     }
     u->p2p = true;
-    return MMF_OK;
+    return uniform_build_tile_orders(ctx);
 }
 
 static void comm_ipc_close(mmf_ctx *ctx)
@@ -374,7 +375,7 @@ static void comm_ipc_close(mmf_ctx *ctx)
     u->p2p = false;
 }
 
-static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S)
+static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
@@ -383,28 +384,52 @@ static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S)
     if (a < 0) return fail(ctx, MMF_ERR_STATE, "peer exchange is defined for the U / W arrays only");
     PushArgs args{};
     unsigned int mask = 0;
+    int n_slots = 0;
     for (int s = 0; s < 6; ++s) {
         if (u->nbr_rank[s] < 0) continue;
         args.dst[s] = u->peer_arr[s][a];
         args.flag[s] = u->peer_flags[s];
+        args.side_of_slot[n_slots++] = s;
         mask |= 1u << s;
     }
     if (!mask) return MMF_OK;
     const unsigned long long seq = ++u->xchg_seq;
     const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
-    dim3 grid((na + 255) / 256, nb, 6);
-    uniform_push_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, args, u->push_count, seq);
+    dim3 grid((na + 255) / 256, nb, n_slots);
+    const bool async = defer_wait && u->push_async;
+    cudaStream_t ps = ctx->stream;
+    if (!async) { // pushes share one completion counter: never two in flight
+        for (int q = 0; q < 3; ++q) {
+            if (u->push_pending[q]) {
+                MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
+                u->push_pending[q] = false;
+            }
+        }
+    }
+    if (async) { // next to the interior tiles of the following stage
+        MMF_CUDA(ctx, cudaEventRecord(u->ev_stage, ctx->stream));
+        MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, u->ev_stage, 0));
+        ps = ctx->comm_stream;
+    }
+    uniform_push_kernel<<<grid, 256, 0, ps>>>(g, S, args, u->push_count, seq);
     MMF_LAUNCH_CHECK(ctx);
-    uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
-    MMF_LAUNCH_CHECK(ctx);
+    if (async) {
+        MMF_CUDA(ctx, cudaEventRecord(u->ev_push[a], ctx->comm_stream));
+        u->push_pending[a] = true;
+    }
+    u->arr_seq[a] = seq;
+    if (!defer_wait) { // nobody downstream waits in-kernel: block the stream until all neighbours have delivered
+        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
+        MMF_LAUNCH_CHECK(ctx);
+    }
     return MMF_OK;
 }
 
-int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S)
+int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
 {
     Comm *c = ctx->comm;
     UniformPath *u = ctx->uni;
-    if (u->p2p) return comm_uniform_push_enqueue(ctx, S);
+    if (u->p2p) return comm_uniform_push_enqueue(ctx, S, defer_wait);
     const UniformGeom &g = u->g;
     bool any = false;
     for (int s = 0; s < 6; ++s) {
@@ -441,7 +466,7 @@ int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S)
 
 static int comm_exchange_enqueue(mmf_ctx *ctx, int field)
 {
-    if (ctx->path == MMF_PATH_UNIFORM) return comm_uniform_exchange_enqueue(ctx, uniform_field_ptr(ctx, field));
+    if (ctx->path == MMF_PATH_UNIFORM) return comm_uniform_exchange_enqueue(ctx, uniform_field_ptr(ctx, field), false);
     return comm_generic_exchange_enqueue(ctx, ctx->fields[field]);
 }
 

@@ -172,7 +172,11 @@ static int create_common(mmf_ctx *ctx, int device)
     ctx->device = device;
     ctx->tracing = getenv("MMF_TRACE") && atoi(getenv("MMF_TRACE")) != 0;
     MMF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    MMF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0; // the communication stream gets the highest priority: its (small) kernels are
+        MMF_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi)); // dispatched ahead of pending stage CTAs
+        MMF_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    }
     MMF_CUDA(ctx, cudaEventCreate(&ctx->ev_start));
     MMF_CUDA(ctx, cudaEventCreate(&ctx->ev_stop));
     int rc = dev_alloc(ctx, &ctx->d_ctl, 1);
@@ -237,6 +241,7 @@ extern "C" int mmf_destroy(mmf_ctx *ctx)
     if (!ctx) return MMF_OK;
     if (ctx->device >= 0) cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     trace_report(ctx);
     comm_destroy(ctx);
     uniform_destroy(ctx);

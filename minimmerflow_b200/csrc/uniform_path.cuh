@@ -48,6 +48,16 @@ struct UniformPath {
     unsigned long long *peer_flags[6] = {};
     unsigned int *push_count = nullptr;             // blocks of the running push kernel that are done
     unsigned long long xchg_seq = 0;
+    unsigned long long arr_seq[3] = { 0, 0, 0 }; // exchange that last refreshed the ghosts of U / Wa / Wb
+    bool halo_inkernel = false;       // boundary CTAs of the stage kernels wait for the neighbours themselves
+    int *tile_order[4] = {};          // per stage shape: interior tiles first, tiles on a partition side last
+    // the push of a stage's output runs on the communication stream, next to the interior tiles of the
+    // following stage; allowed only when every stage has at least one full wave of interior tiles, so
+    // that waiting boundary CTAs can never hold all SMs before the push has been scheduled
+    bool push_async = false;
+    cudaEvent_t ev_stage = nullptr;           // the stage whose output is to be pushed has finished
+    cudaEvent_t ev_push[3] = {};              // the last push that read U / Wa / Wb has finished
+    bool push_pending[3] = { false, false, false };
     void *ipc_opened[6][4] = {};
 };
 
@@ -56,6 +66,10 @@ inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_c
 
 inline void uniform_destroy(mmf_ctx *ctx)
 {
+    if (ctx->uni) {
+        if (ctx->uni->ev_stage) cudaEventDestroy(ctx->uni->ev_stage);
+        for (cudaEvent_t e : ctx->uni->ev_push) if (e) cudaEventDestroy(e);
+    }
     delete ctx->uni;
     ctx->uni = nullptr;
 }
@@ -95,6 +109,35 @@ static LoadClamp uniform_load_clamp(const UniformPath *u)
     return lc;
 }
 
+// visiting order of the tiles of every stage shape: tiles that touch no partition side first
+static int uniform_build_tile_orders(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    u->push_async = u->halo_inkernel && !(getenv("MMF_PUSH_SYNC") && atoi(getenv("MMF_PUSH_SYNC")));
+    for (int st = 0; st < 4; ++st) {
+        const StageShape &sh = u->shape[st];
+        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + sh.nw - 3) / (sh.nw - 2), tz = (g.nz + sh.lz - 1) / sh.lz;
+        std::vector<int> inner, outer;
+        for (int t = 0; t < tx * ty * tz; ++t) {
+            const int bx = t % tx, by = (t / tx) % ty, bz = t / (tx * ty);
+            const bool side[6] = { bx == 0, bx == tx - 1, by == 0, by == ty - 1, bz == 0, bz == tz - 1 };
+            bool waits = false;
+            for (int s = 0; s < 6; ++s) waits = waits || (side[s] && u->nbr_rank[s] >= 0);
+            (waits ? outer : inner).push_back(t);
+        }
+        if (st >= 1) u->push_async = u->push_async && (int) inner.size() >= ctx->prop.multiProcessorCount;
+        inner.insert(inner.end(), outer.begin(), outer.end());
+        int rc = dev_upload(ctx, &u->tile_order[st], inner);
+        if (rc) return rc;
+    }
+    if (u->push_async && !u->ev_stage) {
+        MMF_CUDA(ctx, cudaEventCreateWithFlags(&u->ev_stage, cudaEventDisableTiming));
+        for (int a = 0; a < 3; ++a) MMF_CUDA(ctx, cudaEventCreateWithFlags(&u->ev_push[a], cudaEventDisableTiming));
+    }
+    return MMF_OK;
+}
+
 template <typename K>
 static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
 {
@@ -123,10 +166,29 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double 
     // record (11) + flux (5) doubles per lane and row, two mbarriers per row
     const size_t smem = (size_t) nw * smem_doubles_per_lane * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    for (int q = 0; q < 3; ++q) {
+        if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
+            MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
+            u->push_pending[q] = false;
+        }
+    }
+    HaloWait hw{};
+    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
+    if (ctx->comm && u->p2p && u->halo_inkernel) {
+        int a = -1;
+        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
+        for (int s = 0; s < 6; ++s) hw.mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
+        if (a >= 0 && hw.mask) {
+            hw.flags = u->flags;
+            hw.seq = u->arr_seq[a];
+            hw.tile_order = u->tile_order[stage];
+            if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+        }
+    }
     {
         ScopedLaunchTimer timer(ctx, stage);
         kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u));
+                                                   uniform_load_clamp(u), hw);
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -160,7 +222,7 @@ static int launch_stage(mmf_ctx *ctx, const double *Sin, const double *Un, doubl
     }
 }
 
-int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S); // comm.cuh
+int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S, bool defer_wait); // comm.cuh
 
 // refresh the ghost shell of a padded array: physical sides from the BC, partition sides by exchange
 static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, double *eig_next = nullptr)
@@ -176,7 +238,9 @@ static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, dou
         uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next, skip_ff);
         MMF_LAUNCH_CHECK(ctx);
     }
-    if (ctx->comm) return comm_uniform_exchange_enqueue(ctx, S);
+    trace_point(ctx, "bc");
+    // inside a fused step the consumer (the next stage kernel) waits for the neighbours itself
+    if (ctx->comm) return comm_uniform_exchange_enqueue(ctx, S, check_active && ctx->uni->halo_inkernel);
     return MMF_OK;
 }
 
@@ -222,6 +286,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // derives for its first z interface; chunks stay between 16 and 96 planes.
     u->clamp_ff = true;
     for (int st = 0; st < 4; ++st) u->clamp_ff = u->clamp_ff && u->shape[st].form != '3';
+    u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));
     const char *env_lz = getenv("MMF_STAGE_LZ");
     for (int st = 0; st < 4; ++st) {
         StageShape &sh = u->shape[st];
@@ -452,6 +517,12 @@ static int uniform_scatter_state(mmf_ctx *ctx, int field, const double *staging)
     int rc;
     if (field == MMF_FIELD_RHS && (rc = uniform_ensure_rhs(ctx))) return rc;
     double *S = uniform_field_ptr(ctx, field);
+    for (int q = 0; q < 3; ++q) {
+        if (S == u->arr[q] && u->push_pending[q]) {
+            MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
+            u->push_pending[q] = false;
+        }
+    }
     uniform_scatter_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
         u->g, u->cell_numbering, u->cell_off, staging, S, ctx->n_cells);
     MMF_LAUNCH_CHECK(ctx);

@@ -104,11 +104,52 @@ __device__ __forceinline__ void finish_plane(const double *S, const double *AFz,
     }
 }
 
+// which tile of the box a CTA works on: the block index, or -- multi-GPU with peer stores -- the entry
+// of the interior-first visiting order
+struct TileId {
+    int bx, by, bz, tile;
+};
+
+__device__ __forceinline__ TileId stage_tile(const HaloWait &hw)
+{
+    TileId t;
+    if (hw.tile_order) {
+        t.tile = hw.tile_order[blockIdx.x];
+        t.bx = t.tile % hw.tx;
+        t.by = (t.tile / hw.tx) % hw.ty;
+        t.bz = t.tile / (hw.tx * hw.ty);
+    } else {
+        t.bx = blockIdx.x; t.by = blockIdx.y; t.bz = blockIdx.z;
+        t.tile = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    }
+    return t;
+}
+
+// CTAs on a partition side wait for the neighbours' layers of the array they are about to read
+// (the counters are raised by uniform_push_kernel on the neighbour GPUs, comm.cuh)
+__device__ __forceinline__ void halo_wait(const HaloWait &hw, const TileId &t)
+{
+    if (!hw.flags) return;
+    unsigned int touched = 0;
+    if (t.bx == 0) touched |= 1u;
+    if (t.bx == hw.tx - 1) touched |= 2u;
+    if (t.by == 0) touched |= 4u;
+    if (t.by == hw.ty - 1) touched |= 8u;
+    if (t.bz == 0) touched |= 16u;
+    if (t.bz == hw.tz - 1) touched |= 32u;
+    const unsigned int need = touched & hw.mask;
+    if (need && threadIdx.x < 6 && ((need >> threadIdx.x) & 1u)) {
+        const volatile unsigned long long *f = hw.flags + threadIdx.x;
+        while (*f < hw.seq) { }
+        __threadfence_system();
+    }
+}
+
 // block-wide maxima at the end of a stage kernel: the face eigenvalue (warp shuffle, one value per
 // warp through shared memory, one integer atomic per CTA) and, for stage 3, the CTA's eigenvalue
 // estimate, stored per CTA (no atomic)
 template <int NW>
-__device__ __forceinline__ void block_maxima(double v, double *out, float est, float *cta_est, double *scratch)
+__device__ __forceinline__ void block_maxima(double v, double *out, float est, float *cta_est, int tile, double *scratch)
 {
     const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
     __syncthreads(); // every warp is done with the exchange buffers
@@ -130,7 +171,7 @@ __device__ __forceinline__ void block_maxima(double v, double *out, float est, f
         }
         if (lane == 0) {
             atomic_max_nonneg(out, a);
-            if (cta_est) cta_est[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (float) b;
+            if (cta_est) cta_est[tile] = (float) b;
         }
     }
 }
@@ -222,7 +263,7 @@ struct RowCtx {
         //      exposed in every plane, 15 % of all stall samples in profiles/r01b).
         if (kz + 1 <= khi) sp += plane;
 #pragma unroll
-        for (int k = 0; k < NF; ++k) P.U[k] = sp[k * fs];
+        for (int k = 0; k < NF; ++k) P.U[k] = ldsin(sp + k * fs);
         {
             double lU[NF], lF[NF];
 #pragma unroll
@@ -303,7 +344,7 @@ template <int STAGE, int ORDER, int NW>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                        float *__restrict__ cta_est, const LoadClamp lc)
+                        float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -316,15 +357,17 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
 
     const int lane = threadIdx.x & 31;
     const int row  = threadIdx.x >> 5;
+    const TileId tid = stage_tile(hw);
     if (threadIdx.x < NW) {
         mbar_init(&barD[threadIdx.x], 1);
         mbar_init(&barF[threadIdx.x], 1);
     }
+    halo_wait(hw, tid);
     __syncthreads();
 
-    const int i  = blockIdx.x * XW - 1 + lane;
-    const int j  = blockIdx.y * (NW - 2) - 1 + row;
-    const int z0 = blockIdx.z * lz;
+    const int i  = tid.bx * XW - 1 + lane;
+    const int j  = tid.by * (NW - 2) - 1 + row;
+    const int z0 = tid.bz * lz;
     const int z1 = min(z0 + lz, g.nz);
     const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
     const int jc = min(max(j, lc.jlo), lc.jhi);
@@ -349,7 +392,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         double *d = sm_d + lane;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
@@ -358,7 +401,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
             sp += plane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -379,7 +422,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         double lmy = 0.0;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
@@ -388,7 +431,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
             sp += plane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -443,10 +486,10 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) A.U[k] = c.sp[k * fs];
+            for (int k = 0; k < NF; ++k) A.U[k] = ldsin(c.sp + k * fs);
             c.sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
 #pragma unroll
-            for (int k = 0; k < NF; ++k) B.U[k] = c.sp[k * fs];
+            for (int k = 0; k < NF; ++k) B.U[k] = ldsin(c.sp + k * fs);
             CellPrim q;
             derive_cell(A.U, dc, q);
             axis_flux<2>(q, A.Fz, A.lz);
@@ -473,7 +516,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         emax = c.est_max;
     }
 
-    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, smem);
+    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, tid.tile, smem);
 }
 
 } // namespace mmf

@@ -15,7 +15,7 @@ template <int STAGE, int ORDER, int NW>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                          const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                         float *__restrict__ cta_est, const LoadClamp lc)
+                         float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -28,15 +28,17 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
 
     const int lane = threadIdx.x & 31;
     const int row  = threadIdx.x >> 5;
+    const TileId tid = stage_tile(hw);
     if (threadIdx.x < NW) {
         mbar_init(&barD[threadIdx.x], 1);
         mbar_init(&barF[threadIdx.x], 1);
     }
+    halo_wait(hw, tid);
     __syncthreads();
 
-    const int i  = blockIdx.x * XW - 1 + lane;
-    const int j  = blockIdx.y * (NW - 2) - 1 + row;
-    const int z0 = blockIdx.z * lz;
+    const int i  = tid.bx * XW - 1 + lane;
+    const int j  = tid.by * (NW - 2) - 1 + row;
+    const int z0 = tid.bz * lz;
     const int z1 = min(z0 + lz, g.nz);
     const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
     const int jc = min(max(j, lc.jlo), lc.jhi);
@@ -61,7 +63,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         double *d = sm_d + lane;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
@@ -70,7 +72,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             sp += plane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -91,7 +93,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         double lmy = 0.0;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
@@ -100,7 +102,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             sp += plane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -144,10 +146,10 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) pU[k] = sp[k * fs];
+            for (int k = 0; k < NF; ++k) pU[k] = ldsin(sp + k * fs);
             sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
 #pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             CellPrim q;
             derive_cell(pU, dc, q);
             axis_flux<2>(q, pFz, plz);
@@ -162,7 +164,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
             if (kz + 1 <= lc.khi) sp += plane; // plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side)
 #pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = sp[k * fs];
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
             double cUn[NF];
             if (STAGE >= 2 && upd) {
 #pragma unroll
@@ -300,7 +302,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         emax = est_max;
     }
 
-    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, smem);
+    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, tid.tile, smem);
 }
 
 } // namespace mmf
