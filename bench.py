@@ -190,7 +190,7 @@ def run_reference(args):
 def workload_config(S, gdims, grid):
     return {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
                         f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
-            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: direct peer stores over NVLink, scalar all-reduce: NCCL)",
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: direct peer stores over NVLink overlapped with interior tiles, scalar all-reduce: NCCL)",
             "path": "uniform fused stage kernels",
             "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
 
