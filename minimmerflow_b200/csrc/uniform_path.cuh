@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 namespace mmf {
 
@@ -109,6 +110,19 @@ static LoadClamp uniform_load_clamp(const UniformPath *u)
     return lc;
 }
 
+// opt-in to more than 48 KB of dynamic shared memory, once per kernel and device
+template <typename K>
+static cudaError_t stage_smem_attribute(K kern, size_t smem)
+{
+    static std::vector<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const auto &d : done) if (d.first == (const void *) kern && d.second == dev) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess) done.emplace_back((const void *) kern, dev);
+    return e;
+}
+
 // visiting order of the tiles of every stage shape: tiles that touch no partition side first
 static int uniform_build_tile_orders(mmf_ctx *ctx)
 {
@@ -146,7 +160,7 @@ static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, c
     const int nw = 12, lz = u->shape[stage].lz;
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
     const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
-    MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     {
         ScopedLaunchTimer timer(ctx, stage);
         kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz);
@@ -165,7 +179,7 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double 
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
     // record (11) + flux (5) doubles per lane and row, two mbarriers per row
     const size_t smem = (size_t) nw * smem_doubles_per_lane * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
-    MMF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     for (int q = 0; q < 3; ++q) {
         if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
             MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
