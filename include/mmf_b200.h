@@ -222,11 +222,11 @@ int mmf_comm_set_box_neighbours(mmf_ctx *ctx, const int32_t neighbour_ranks[6]);
 /* Uniform path, optional: exchange halos by DIRECT PEER STORES over NVLink instead of NCCL
  * send/recv + pack/unpack (the role of the send / receive buffers of bitpit's DataCommunicator,
  * src/communications.cpp:282-322, disappears).  Every rank exports MMF_IPC_BLOB_BYTES bytes (CUDA IPC
- * handles of its state arrays and arrival counters), the host gathers the blobs of all ranks in rank
+ * handles of its state arrays, arrival counters and x ghost columns), the host gathers the blobs of all ranks in rank
  * order (MPI_Allgather / torch.distributed) and hands the concatenation to every rank.  Requires one
  * process per GPU on one node, equal box dimensions on all ranks, and mmf_comm_set_box_neighbours
  * before the import. */
-#define MMF_IPC_BLOB_BYTES 256
+#define MMF_IPC_BLOB_BYTES 512
 int mmf_comm_ipc_export(mmf_ctx *ctx, void *blob_out);
 int mmf_comm_ipc_import(mmf_ctx *ctx, const void *all_ranks_blobs);
 /* startAllExchanges + completeAllExchanges (src/communications.cpp:375-470; call sites

@@ -257,7 +257,10 @@ static int comm_set_box_neighbours(mmf_ctx *ctx, const int32_t ranks[6])
 // then raises this rank's arrival counter in every neighbour.  The consumer is a one-warp kernel in
 // front of the next stage that waits for the counters of all its neighbours.
 struct PushArgs {
-    double *dst[6];               // neighbour's array (same field layout, same box dimensions)
+    double *dst[6];               // neighbour's array (same field layout, same box dimensions), or -- x sides
+                                  // with compact_x -- the neighbour's compact ghost columns for this array
+    int compact_x;                // x layers go to [field][k+1][j+1] columns (XGhost) instead of the padded array
+    long long xg_fs;
     unsigned long long *flag[6];  // neighbour's arrival counter for the side this rank sits on
     int side_of_slot[6];          // blockIdx.z -> side: only sides that have a neighbour are launched
 };
@@ -279,8 +282,14 @@ __global__ void __launch_bounds__(256) uniform_push_kernel(const UniformGeom g, 
             else if (axis == 1) { so = uoff(g, a, own, b); go = uoff(g, a, ghost, b); }
             else                { so = uoff(g, a, b, own); go = uoff(g, a, b, ghost); }
             double *d = args.dst[side];
+            if (axis == 0 && args.compact_x) { // contiguous in j: coalesced stores over NVLink
+                const long long co = (long long) (b + 1) * (g.ny + 2) + (a + 1);
 #pragma unroll
-            for (int f = 0; f < NF; ++f) d[f * g.fs + go] = S[f * g.fs + so];
+                for (int f = 0; f < NF; ++f) d[f * args.xg_fs + co] = S[f * g.fs + so];
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) d[f * g.fs + go] = S[f * g.fs + so];
+            }
         }
     }
     // last block out raises the arrival counters: every block's stores are fenced at system scope
@@ -312,7 +321,9 @@ __global__ void uniform_wait_kernel(const unsigned long long *flags, unsigned in
     __threadfence_system();
 }
 
-constexpr size_t IPC_BLOB_BYTES = 4 * sizeof(cudaIpcMemHandle_t);
+constexpr int IPC_HANDLES = 5; // U, Wa, Wb, arrival counters, compact x ghost columns
+constexpr size_t IPC_BLOB_BYTES = 512; // = MMF_IPC_BLOB_BYTES
+static_assert(IPC_HANDLES * sizeof(cudaIpcMemHandle_t) <= IPC_BLOB_BYTES, "IPC blob too small");
 
 static int comm_ipc_export(mmf_ctx *ctx, void *out)
 {
@@ -324,10 +335,20 @@ static int comm_ipc_export(mmf_ctx *ctx, void *out)
         if ((rc = dev_alloc(ctx, &u->push_count, 1))) return rc;
         MMF_CUDA(ctx, cudaMemset(u->flags, 0, 8 * sizeof(unsigned long long)));
         MMF_CUDA(ctx, cudaMemset(u->push_count, 0, sizeof(unsigned int)));
+        // compact x ghost columns: [side][array][field][nz+2][ny+2], initialised with a benign state
+        u->xg_fs = ((long long) (u->g.ny + 2) * (u->g.nz + 2) + 15) / 16 * 16;
+        if ((rc = dev_alloc(ctx, &u->xghost, (size_t) 6 * NF * u->xg_fs))) return rc;
+        for (int q = 0; q < 6; ++q) {
+            fill_benign_kernel<<<grid_for(u->xg_fs, 256), 256, 0, ctx->stream>>>(u->xghost + (size_t) q * NF * u->xg_fs, u->xg_fs);
+            MMF_LAUNCH_CHECK(ctx);
+        }
+        MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    memset(out, 0, IPC_BLOB_BYTES);
     cudaIpcMemHandle_t *h = static_cast<cudaIpcMemHandle_t *>(out);
     for (int a = 0; a < 3; ++a) MMF_CUDA(ctx, cudaIpcGetMemHandle(&h[a], u->arr[a]));
     MMF_CUDA(ctx, cudaIpcGetMemHandle(&h[3], u->flags));
+    MMF_CUDA(ctx, cudaIpcGetMemHandle(&h[4], u->xghost));
     return MMF_OK;
 }
 
@@ -345,7 +366,7 @@ static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
         if (r == c->rank) return fail(ctx, MMF_ERR_INVALID, "mmf_comm_ipc_import: a box cannot neighbour itself");
         const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(blob + (size_t) r * IPC_BLOB_BYTES);
         // the same neighbour may sit on several sides only in degenerate grids; open per side anyway
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < IPC_HANDLES; ++a) {
             void *p = nullptr;
             bool reused = false;
             for (int s2 = 0; s2 < s && !reused; ++s2) {
@@ -357,8 +378,9 @@ static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
                 MMF_CUDA(ctx, cudaIpcOpenMemHandle(&p, hh, cudaIpcMemLazyEnablePeerAccess));
                 u->ipc_opened[s][a] = p;
             }
-            if (a < 3) u->peer_arr[s][a] = static_cast<double *>(p);
-            else       u->peer_flags[s] = static_cast<unsigned long long *>(p) + (s ^ 1); // I sit on its opposite side
+            if (a < 3)       u->peer_arr[s][a] = static_cast<double *>(p);
+            else if (a == 3) u->peer_flags[s] = static_cast<unsigned long long *>(p) + (s ^ 1); // I sit on its opposite side
+            else             u->peer_xghost[s] = static_cast<double *>(p);
         }
     }
     u->p2p = true;
@@ -370,7 +392,7 @@ static void comm_ipc_close(mmf_ctx *ctx)
     UniformPath *u = ctx->uni;
     if (!u) return;
     for (int s = 0; s < 6; ++s)
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < IPC_HANDLES; ++a)
             if (u->ipc_opened[s][a]) { cudaIpcCloseMemHandle(u->ipc_opened[s][a]); u->ipc_opened[s][a] = nullptr; }
     u->p2p = false;
 }
@@ -385,9 +407,15 @@ static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
     PushArgs args{};
     unsigned int mask = 0;
     int n_slots = 0;
+    // compact x ghost columns only where the readers know about them (v5 stage kernels with in-kernel waits)
+    args.compact_x = uniform_use_xghost(ctx) ? 1 : 0;
+    args.xg_fs = u->xg_fs;
     for (int s = 0; s < 6; ++s) {
         if (u->nbr_rank[s] < 0) continue;
         args.dst[s] = u->peer_arr[s][a];
+        if (s < 2 && args.compact_x) { // my -x layer is the +x ghost column of the neighbour, and vice versa
+            args.dst[s] = u->peer_xghost[s] + (size_t) (((s ^ 1) & 1) * 3 + a) * NF * u->xg_fs;
+        }
         args.flag[s] = u->peer_flags[s];
         args.side_of_slot[n_slots++] = s;
         mask |= 1u << s;

@@ -48,6 +48,10 @@ struct UniformPath {
     unsigned long long *flags = nullptr;            // [6] arrival counters, written by the neighbours
     unsigned long long *peer_flags[6] = {};
     unsigned int *push_count = nullptr;             // blocks of the running push kernel that are done
+    // compact ghost columns for x partition sides (XGhost): one allocation, [side 0/1][array U/Wa/Wb]
+    double *xghost = nullptr;
+    double *peer_xghost[6] = {};
+    long long xg_fs = 0;
     unsigned long long xchg_seq = 0;
     unsigned long long arr_seq[3] = { 0, 0, 0 }; // exchange that last refreshed the ghosts of U / Wa / Wb
     bool halo_inkernel = false;       // boundary CTAs of the stage kernels wait for the neighbours themselves
@@ -59,7 +63,7 @@ struct UniformPath {
     cudaEvent_t ev_stage = nullptr;           // the stage whose output is to be pushed has finished
     cudaEvent_t ev_push[3] = {};              // the last push that read U / Wa / Wb has finished
     bool push_pending[3] = { false, false, false };
-    void *ipc_opened[6][4] = {};
+    void *ipc_opened[6][5] = {};
 };
 
 inline int uniform_order_exact(const mmf_ctx *ctx) { return ctx->uni ? ctx->uni->order_exact : 0; }
@@ -94,6 +98,16 @@ static int uniform_ensure_rhs(mmf_ctx *ctx)
 }
 
 // ---- launch helpers -----------------------------------------------------------------------------
+
+// compact x ghost columns are read by the XG = true instantiations, built for the default CTA shapes only
+static bool uniform_use_xghost(const mmf_ctx *ctx)
+{
+    const UniformPath *u = ctx->uni;
+    if (!(ctx->comm && u->p2p && u->halo_inkernel && u->xghost)) return false;
+    if (u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0) return false;
+    for (int st = 0; st < 4; ++st) if (u->shape[st].nw != 12 && u->shape[st].nw != 16) return false;
+    return true;
+}
 
 // free-flow sides: the v5 stage kernels re-read the boundary cell instead of a ghost cell
 static LoadClamp uniform_load_clamp(const UniformPath *u)
@@ -199,10 +213,19 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double 
             if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
         }
     }
+    XGhost xg{};
+    if (hw.flags && uniform_use_xghost(ctx)) { // x ghosts of partition sides come from the compact columns
+        int a = 0;
+        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
+        xg.fs = u->xg_fs;
+        xg.pitch = g.ny + 2;
+        if (u->nbr_rank[0] >= 0) xg.lo = u->xghost + (size_t) (0 * 3 + a) * NF * u->xg_fs;
+        if (u->nbr_rank[1] >= 0) xg.hi = u->xghost + (size_t) (1 * 3 + a) * NF * u->xg_fs;
+    }
     {
         ScopedLaunchTimer timer(ctx, stage);
         kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u), hw);
+                                                   uniform_load_clamp(u), hw, xg);
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -214,16 +237,21 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     UniformPath *u = ctx->uni;
     const StageShape sh = u->shape[STAGE];
     if (sh.form == '3') return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
+    const bool xgk = uniform_use_xghost(ctx);
+#define MMF_LAUNCH(KERN, NWV, XGV) return launch_stage_k(ctx, KERN<STAGE, ORDER, NWV, XGV>, STAGE, NWV, Sin, Un, Out, d_max)
     if (sh.form == 'r') {
-        if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
-        if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
-        if (sh.nw == 10) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 10>, STAGE, 10, Sin, Un, Out, d_max);
-        return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
+        if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5r, 16, false); }
+        if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5r, 8, false);
+        if (sh.nw == 10) MMF_LAUNCH(uniform_stage_kernel_v5r, 10, false);
+        if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 12, true);
+        MMF_LAUNCH(uniform_stage_kernel_v5r, 12, false);
     }
-    if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 16>, STAGE, 16, Sin, Un, Out, d_max);
-    if (sh.nw == 8) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 8>, STAGE, 8, Sin, Un, Out, d_max);
-    if (sh.nw == 10) return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 10>, STAGE, 10, Sin, Un, Out, d_max);
-    return launch_stage_k(ctx, uniform_stage_kernel_v5<STAGE, ORDER, 12>, STAGE, 12, Sin, Un, Out, d_max);
+    if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5, 16, false); }
+    if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5, 8, false);
+    if (sh.nw == 10) MMF_LAUNCH(uniform_stage_kernel_v5, 10, false);
+    if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 12, true);
+    MMF_LAUNCH(uniform_stage_kernel_v5, 12, false);
+#undef MMF_LAUNCH
 }
 
 template <int STAGE>
@@ -267,7 +295,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     g.py = g.ny + 2;
     g.pz = g.nz + 2;
     g.fs = ((long long) g.px * g.py * g.pz + 15) / 16 * 16;
-    if (g.fs * NF >= ((long long) 1 << 31) * 4) return fail(ctx, MMF_ERR_INVALID, "uniform box too large");
+    // the stage kernels index one field with 32-bit element offsets (4 field strides must stay below 2^31)
+    if (g.fs * (NF - 1) >= ((long long) 1 << 31)) return fail(ctx, MMF_ERR_INVALID, "uniform box too large for one GPU (> 536 M padded cells)");
     int rc;
     for (int a = 0; a < 3; ++a) {
         if ((rc = dev_alloc(ctx, &u->arr[a], (size_t) NF * g.fs))) return rc;

@@ -200,7 +200,8 @@ struct RowCtx {
     int lane, key_x, key_y, gz0, khi;
     double dt, Ah, volume;
     DivConsts dc;
-    long long fs, plane;
+    long long fs, plane;   // own cells: U^n loads and stores
+    long long sfs, splane; // this lane's column of the residual input (padded array or compact x ghosts)
     double *d_own, *f_own;
     const double *d_dn, *f_up;
     unsigned long long *barD_own, *barD_dn, *barF_own, *barF_up;
@@ -261,9 +262,9 @@ struct RowCtx {
         //      hoist the loads above it into the live range of the old values, which made it park the
         //      results in other registers and copy them right behind the loads (a DRAM round trip
         //      exposed in every plane, 15 % of all stall samples in profiles/r01b).
-        if (kz + 1 <= khi) sp += plane;
+        if (kz + 1 <= khi) sp += splane;
 #pragma unroll
-        for (int k = 0; k < NF; ++k) P.U[k] = ldsin(sp + k * fs);
+        for (int k = 0; k < NF; ++k) P.U[k] = ldsin(sp + k * sfs);
         {
             double lU[NF], lF[NF];
 #pragma unroll
@@ -340,11 +341,11 @@ struct RowCtx {
     }
 };
 
-template <int STAGE, int ORDER, int NW>
+template <int STAGE, int ORDER, int NW, bool XG>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                        float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw)
+                        float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw, const XGhost xg)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -383,25 +384,36 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
     const long long plane = (long long) g.py * g.px;
     const long long fs    = g.fs;
     const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
+    // where this lane's column of the residual input lives: the padded array, or -- halo lanes across an
+    // x partition side -- the compact ghost columns
+    const double *scol = Sin + col;
+    // (XG = false instantiations keep the strides uniform: per-lane strides cost registers the
+    //  single-GPU kernels do not have to spare)
+    int sfs_lane = (int) fs, splane_lane = (int) plane; // element counts: < 2^31 for any box that fits one GPU
+    if (XG) {
+        if (xg.lo && i < 0)     { scol = xg.lo + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+        if (xg.hi && i >= g.nx) { scol = xg.hi + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+    }
+    const long long sfs = XG ? (long long) sfs_lane : fs, splane = XG ? (long long) splane_lane : plane;
     double lmax = 0.0;
     float emax = 0.f;
 
     if (row == 0) {
         // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
-        const double *sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
         double *d = sm_d + lane;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane;
+            sp += splane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -416,22 +428,22 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
     } else if (row == NW - 1) {
         // ================= high halo row: computes the y face (j-1 | j) for row NW-2 ================
         const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;
-        const double *sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
         const double *d_dn = sm_d + (NW - 2) * 11 * 32 + lane;
         double *f = sm_f + (NW - 1) * NF * 32 + lane;
         double lmy = 0.0;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane;
+            sp += splane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -465,6 +477,8 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         c.khi   = lc.khi;
         c.fs    = fs;
         c.plane = plane;
+        c.sfs   = sfs;
+        c.splane = splane;
         c.d_own = sm_d + row * 11 * 32 + lane;
         c.d_dn  = sm_d + (row - 1) * 11 * 32 + lane;
         c.f_own = sm_f + row * NF * 32 + lane;
@@ -473,7 +487,7 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         c.barD_dn  = &barD[row - 1];
         c.barF_own = &barF[row];
         c.barF_up  = &barF[row + 1];
-        c.sp  = Sin + col + (long long) (max(z0 - 1, lc.klo) + 1) * plane; // plane z0-1 (clamped)
+        c.sp  = scol + (long long) (max(z0 - 1, lc.klo) + 1) * splane; // plane z0-1 (clamped)
         c.unp = Un + col + (long long) (z0 + 1) * plane;   // plane z0
         c.op  = Out + col + (long long) z0 * plane;        // plane z0-1 (the first store goes to plane z0)
         c.lmx = c.lmy = c.lmz = 0.0;
@@ -486,10 +500,10 @@ uniform_stage_kernel_v5(const UniformGeom g, const double *__restrict__ Sin, con
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) A.U[k] = ldsin(c.sp + k * fs);
-            c.sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+            for (int k = 0; k < NF; ++k) A.U[k] = ldsin(c.sp + k * sfs);
+            c.sp = scol + (long long) (z0 + 1) * splane; // plane z0
 #pragma unroll
-            for (int k = 0; k < NF; ++k) B.U[k] = ldsin(c.sp + k * fs);
+            for (int k = 0; k < NF; ++k) B.U[k] = ldsin(c.sp + k * sfs);
             CellPrim q;
             derive_cell(A.U, dc, q);
             axis_flux<2>(q, A.Fz, A.lz);

@@ -19,11 +19,11 @@ namespace mmf {
 #endif
 constexpr int R_UNROLL = MMF_R_UNROLL;
 
-template <int STAGE, int ORDER, int NW>
+template <int STAGE, int ORDER, int NW, bool XG>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                          const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                         float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw)
+                         float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw, const XGhost xg)
 {
     extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
@@ -62,25 +62,36 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
     const long long plane = (long long) g.py * g.px;
     const long long fs    = g.fs;
     const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
+    // where this lane's column of the residual input lives: the padded array, or -- halo lanes across an
+    // x partition side -- the compact ghost columns
+    const double *scol = Sin + col;
+    // (XG = false instantiations keep the strides uniform: per-lane strides cost registers the
+    //  single-GPU kernels do not have to spare)
+    int sfs_lane = (int) fs, splane_lane = (int) plane; // element counts: < 2^31 for any box that fits one GPU
+    if (XG) {
+        if (xg.lo && i < 0)     { scol = xg.lo + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+        if (xg.hi && i >= g.nx) { scol = xg.hi + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+    }
+    const long long sfs = XG ? (long long) sfs_lane : fs, splane = XG ? (long long) splane_lane : plane;
     double lmax = 0.0;
     float emax = 0.f;
 
     if (row == 0) {
         // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
-        const double *sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
         double *d = sm_d + lane;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane;
+            sp += splane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -95,22 +106,22 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
     } else if (row == NW - 1) {
         // ================= high halo row: computes the y face (j-1 | j) for row NW-2 ================
         const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;
-        const double *sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
         const double *d_dn = sm_d + (NW - 2) * 11 * 32 + lane;
         double *f = sm_f + (NW - 1) * NF * 32 + lane;
         double lmy = 0.0;
         double nxt[NF];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
         for (int kz = z0; kz < z1; ++kz) {
             const int it = kz - z0;
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            sp += plane;
+            sp += splane;
             if (kz + 1 < z1) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             }
             CellPrim q;
             derive_cell(cU, dc, q);
@@ -145,8 +156,8 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         double *f_own = sm_f + row * NF * 32 + lane;
         const double *f_up = sm_f + (row + 1) * NF * 32 + lane;
 
-        const double *sp  = Sin + col + (long long) (max(z0 - 1, lc.klo) + 1) * plane; // plane z0-1 (clamped)
-        const double *unp = Un + col + (long long) (z0 + 1) * plane; // plane z0
+        const double *sp  = scol + (long long) (max(z0 - 1, lc.klo) + 1) * splane; // plane z0-1 (clamped)
+        const double *unp = Un + col + (long long) (z0 + 1) * splane; // plane z0
         double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
 
         double pU[NF], pFz[NF], plz, pS[NF], pUn[NF], nxt[NF];
@@ -154,10 +165,10 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) pU[k] = ldsin(sp + k * fs);
-            sp = Sin + col + (long long) (z0 + 1) * plane; // plane z0
+            for (int k = 0; k < NF; ++k) pU[k] = ldsin(sp + k * sfs);
+            sp = scol + (long long) (z0 + 1) * splane; // plane z0
 #pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             CellPrim q;
             derive_cell(pU, dc, q);
             axis_flux<2>(q, pFz, plz);
@@ -171,9 +182,9 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
-            if (kz + 1 <= lc.khi) sp += plane; // plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side)
+            if (kz + 1 <= lc.khi) sp += splane; // plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side)
 #pragma unroll
-            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * fs);
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             double cUn[NF];
             if (STAGE >= 2 && upd) {
 #pragma unroll

@@ -221,7 +221,7 @@ class EulerSolver:
         self._ck(self._lib.mmf_comm_set_ghost_lists(self._h, n, _ptr(ranks, C.c_int32), _ptr(so, C.c_int64),
                                                     _ptr(si, C.c_int64), _ptr(ro, C.c_int64), _ptr(ri, C.c_int64)))
 
-    IPC_BLOB_BYTES = 256
+    IPC_BLOB_BYTES = 512
 
     def comm_ipc_export(self):
         buf = (C.c_char * self.IPC_BLOB_BYTES)()

@@ -60,6 +60,10 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
     h = m["h"]
     if mode.startswith("uniform"):
         grid = box_decomposition(world)
+        if mode.endswith("_x"):
+            grid = (world, 1, 1)       # partition side on x: compact ghost columns (XGhost)
+        elif mode.endswith("_y"):
+            grid = (1, world, 1)
         dims = (n // grid[0], n // grid[1], n // grid[2])
         offset, nbrs = box_of_rank(rank, grid, dims)
         ijk = m["cell_ijk"]
@@ -72,7 +76,7 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
                                     interface_numbering=mmf.NUMBERING_MORTON, global_dims=(n, n, n), box_offset=offset)
         s.comm_init(rank, world, uid)
         s.comm_set_box_neighbours(nbrs)
-        if mode == "uniform_p2p":
+        if mode.startswith("uniform_p2p"):
             _share_ipc(s, rank, world, os.path.join(out_dir, f"ipc_{mode}"))
         s.set_state(mmf.FIELD_U, U[gids])
         n_int = len(gids)
@@ -98,8 +102,10 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
     s.close()
 
 
-@pytest.mark.parametrize("mode,problem", [("uniform_p2p", "vortex_xy"), ("uniform_p2p", "radsod"), ("uniform", "vortex_xy"),
-                                          ("uniform", "radsod"), ("generic", "vortex_xy")])
+@pytest.mark.parametrize("mode,problem", [("uniform_p2p", "vortex_xy"), ("uniform_p2p", "radsod"),
+                                          ("uniform_p2p_x", "vortex_xy"), ("uniform_p2p_x", "radsod"), ("uniform_p2p_y", "radsod"),
+                                          ("uniform", "vortex_xy"), ("uniform", "radsod"), ("uniform_x", "radsod"),
+                                          ("generic", "vortex_xy")])
 def test_two_gpu_run_equals_serial_oracle(mmf, oracle, tmp_path, mode, problem):
     if mmf.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
