@@ -242,13 +242,11 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     if (sh.form == 'r') {
         if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5r, 16, false); }
         if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5r, 8, false);
-        if (sh.nw == 10) MMF_LAUNCH(uniform_stage_kernel_v5r, 10, false);
         if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 12, true);
         MMF_LAUNCH(uniform_stage_kernel_v5r, 12, false);
     }
     if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5, 16, false); }
     if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5, 8, false);
-    if (sh.nw == 10) MMF_LAUNCH(uniform_stage_kernel_v5, 10, false);
     if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 12, true);
     MMF_LAUNCH(uniform_stage_kernel_v5, 12, false);
 #undef MMF_LAUNCH
@@ -318,7 +316,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 10 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
