@@ -184,15 +184,14 @@ static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, c
 }
 
 template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max,
-                          int smem_doubles_per_lane = 16)
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
     const int lz = u->shape[stage].lz;
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
     // record (11) + flux (5) doubles per lane and row, two mbarriers per row
-    const size_t smem = (size_t) nw * smem_doubles_per_lane * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
+    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     for (int q = 0; q < 3; ++q) {
         if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
@@ -302,8 +301,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         MMF_LAUNCH_CHECK(ctx);
     }
     // Launch shapes, measured at 256^3 on B200 (profiles/): the ping-pong form at 16 warps (128
-    // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (166 registers,
-    // no spills) the fastest for stages 2 and 3, which also stream U^n.
+    // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (164-166
+    // registers, no spills) the fastest for stages 2 and 3, which also stream U^n.
     // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "312" = v3 everywhere.
     const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
     for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];

@@ -2,9 +2,9 @@
 // (uniform_stage_v5.cuh explains the scheme): one loop body per plane, the current plane's state is
 // copied into the previous plane's registers at the end of the iteration, U^n is loaded one plane
 // ahead.  Same arithmetic, different register allocation / instruction schedule: measured on B200
-// (profiles/), this form is the faster one for stages 2 and 3 at 12 warps (166 registers, no
-// spills, 0.57 ms at 256^3), the ping-pong form of uniform_stage_v5.cuh for stage 1 at 16 warps
-// (128 registers, 0.52 ms).  uniform_path.cuh picks per stage.
+// (profiles/), this form is the faster one for stages 2 and 3 at 12 warps (164-166 registers, no
+// spills, 0.54 / 0.55 ms at 256^3), the ping-pong form of uniform_stage_v5.cuh for stage 1 at 16
+// warps (128 registers, 0.50 ms).  uniform_path.cuh picks per stage.
 #pragma once
 
 #include "uniform_stage_v5.cuh"

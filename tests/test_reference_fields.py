@@ -62,3 +62,28 @@ def test_fixture_is_current(oracle):
     r = R.run_case(R.REF_EXE, case, want_fields=True)
     assert r["final_error"] == str(ref[case["name"] + "/final_error"])
     assert np.array_equal(r["fields"]["density"], ref[case["name"] + "/density"])
+
+
+@pytest.mark.skipif(not os.path.exists(R.REF_EXE), reason="oracle/_ref/minimmerflow_ref not built (make -C oracle ref)")
+@pytest.mark.parametrize("dim,n", [(2, 8), (3, 4)])
+def test_standin_vtu_is_wellformed(dim, n):
+    """The .vtu the bitpit stand-in writes for the reference's SolverWriter: every cell field has one
+    value (three for velocity) per cell, the connectivity indexes existing points, cells are VTK pixels /
+    voxels of size h, and the initial density of the radial Sod problem takes its two states."""
+    case = dict(problem="radsod", dim=dim, n_cells=n, cfl=0.45, t_end=0.0)
+    r = R.run_case(R.REF_EXE, case, want_fields=True)
+    f = r["fields"]
+    nc = n ** dim
+    assert f["_n_cells"] == nc and r["steps"] == 0
+    for name in ("solved", "pressure", "temperature", "density", "residualC", "residualE"):
+        assert f[name].shape == (nc,)
+    assert f["velocity"].shape == (nc, 3) and f["Points"].shape == ((n + 1) ** dim, 3)
+    vpc = 2 ** dim
+    conn = f["connectivity"].reshape(nc, vpc)
+    assert conn.min() == 0 and conn.max() == (n + 1) ** dim - 1
+    assert np.array_equal(f["offsets"], vpc * np.arange(1, nc + 1))
+    assert set(f["types"]) == {11 if dim == 3 else 8}
+    h = 8.0 / n
+    corners = f["Points"][conn]                                   # [cell, vertex, xyz]
+    assert np.allclose(corners.max(1)[:, :dim] - corners.min(1)[:, :dim], h)
+    assert set(np.round(f["density"], 12)) <= {1.0, 0.125} and f["solved"].min() == 1
