@@ -225,7 +225,8 @@ int mmf_comm_set_box_neighbours(mmf_ctx *ctx, const int32_t neighbour_ranks[6]);
  * handles of its state arrays, arrival counters and x ghost columns), the host gathers the blobs of all ranks in rank
  * order (MPI_Allgather / torch.distributed) and hands the concatenation to every rank.  Requires one
  * process per GPU on one node, equal box dimensions on all ranks, and mmf_comm_set_box_neighbours
- * before the import. */
+ * before the import.  mmf_destroy of such a handle is COLLECTIVE: all ranks must call it (a neighbour
+ * may still be storing into this rank's ghost cells), like freeing a communicator. */
 #define MMF_IPC_BLOB_BYTES 512
 int mmf_comm_ipc_export(mmf_ctx *ctx, void *blob_out);
 int mmf_comm_ipc_import(mmf_ctx *ctx, const void *all_ranks_blobs);

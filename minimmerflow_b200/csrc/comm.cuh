@@ -110,6 +110,17 @@ static void comm_ipc_close(mmf_ctx *ctx);
 static void comm_destroy(mmf_ctx *ctx)
 {
     if (!ctx->comm) return;
+    if (ctx->uni && ctx->uni->p2p && ctx->comm->comm && ctx->d_ctl) {
+        // With peer stores a neighbour may still be writing its last layers into this rank's ghost
+        // cells: tearing a partitioned handle down is collective (like freeing a communicator) -- every
+        // rank first drains its own streams, then all ranks meet in an all-reduce before any mapping goes.
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->comm_stream);
+        if (nccl_api().AllReduce(&ctx->d_ctl->est_max, &ctx->d_ctl->est_max, 1, ncclDouble, ncclMax, ctx->comm->comm,
+                                 ctx->stream) == ncclSuccess) {
+            cudaStreamSynchronize(ctx->stream);
+        }
+    }
     comm_ipc_close(ctx);
     if (ctx->comm->comm) nccl_api().CommDestroy(ctx->comm->comm);
     delete ctx->comm;
