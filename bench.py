@@ -33,7 +33,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--size", type=int, default=256, help="cells per side per GPU (weak scaling)")
+    ap.add_argument("--size", type=int, default=256, help="cells per side: per GPU (weak scaling) or of the whole cube (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one size^3 box per GPU (default, the contract's line); strong: one size^3 cube cut "
+                         "into the N contiguous Morton chunks (SURVEY 8e: 512^3 -> 512x512x256 / 512x256x256 / 256^3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-level", type=int, default=0, help="oracle-port mesh level for the CPU legs (0 = 7)")
     ap.add_argument("--cpu-size", type=int, default=0, help="cells per side for the compiled-reference CPU leg (0 = 128)")
@@ -174,14 +177,14 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     entry, port, (secs, steps) = cpu_baseline_entry(args, cores)
     value = entry["value"]
-    S = args.size
     px, py, pz = box_decomposition(args.gpus)
+    dims, gdims = local_dims(args, (px, py, pz))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": 0 if entry["kind"] == "reference" else 1,
         "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(S, (S * px, S * py, S * pz), (px, py, pz)),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(dims, gdims, (px, py, pz)),
         "cpu_baseline": entry,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,9 +196,19 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(S, gdims, grid):
+def local_dims(args, grid):
+    """Cells per axis of one rank's box, and of the whole mesh."""
+    S = args.size
+    if args.scaling == "strong":
+        if any(S % g for g in grid):
+            raise SystemExit(f"--size {S} is not divisible by the process grid {grid}")
+        return (S // grid[0], S // grid[1], S // grid[2]), (S, S, S)
+    return (S, S, S), (S * grid[0], S * grid[1], S * grid[2])
+
+
+def workload_config(dims, gdims, grid):
     return {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
-                        f"({S}^3 per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
+                        f"({dims[0]}x{dims[1]}x{dims[2]} per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
             "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: direct peer stores over NVLink overlapped with interior tiles, scalar all-reduce: NCCL)",
             "path": "uniform fused stage kernels",
             "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
@@ -218,14 +231,13 @@ def run_ours(args):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
-    S = args.size
     px, py, pz = box_decomposition(world)
     cz, cy, cx = rank // (px * py), (rank // px) % py, rank % px
-    dims = (S, S, S)
-    gdims = (S * px, S * py, S * pz)
-    offset = (cx * S, cy * S, cz * S)
+    dims, gdims = local_dims(args, (px, py, pz))
+    offset = (cx * dims[0], cy * dims[1], cz * dims[2])
+    # h from the x extent: the weak-scaling slabs keep the cell size of the 10-wide cube they grow from
     plane, h = vortex_state(dims, offset, gdims[0])
-    cells_local = S ** 3
+    cells_local = dims[0] * dims[1] * dims[2]
     cells_total = cells_local * world
 
     lib = mmf.load_library()
@@ -233,9 +245,10 @@ def run_ours(args):
     nbytes = cells_local * 5 * 8
     hptr = C.c_void_p()
     mmf._cabi.check(lib.mmf_host_alloc(C.byref(hptr), nbytes))
-    host = np.ctypeslib.as_array((C.c_double * (cells_local * 5)).from_address(hptr.value)).reshape(S, S * S, 5)
+    host = np.ctypeslib.as_array((C.c_double * (cells_local * 5)).from_address(hptr.value)).reshape(
+        dims[2], dims[1] * dims[0], 5)
     flat_plane = plane.reshape(-1, 5)
-    for k in range(S):
+    for k in range(dims[2]):
         host[k] = flat_plane
 
     s = mmf.EulerSolver.uniform(dims, h, [mmf.BC_FREE_FLOW] * 6, device=local_rank,
@@ -329,8 +342,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(S, gdims, (px, py, pz)),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(dims, gdims, (px, py, pz)),
             "clocks": clocks,
             "gpu_launches": int(launches),
             "e2e": {"value": cells_total * 3.0 * args.steps / (e2e_ms * 1e-3), "unit": UNIT,

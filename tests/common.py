@@ -110,3 +110,99 @@ def primitives(oracle, U):
 def dirichlet_info(case):
     """problem::getBorderBCInfo (src/problem.cpp:450-477): only the forward-facing step sets data."""
     return [1.0, 3.0, 0.0, 0.0, 1.0 / 1.4] if case["problem"] == "ffstep" else None
+
+
+def two_level_mesh(dim, n0, refine, H=1.0, bc_code=1, origin=(0.0, 0.0, 0.0)):
+    """A 2:1-balanced two-level octree/quadtree mesh: n0^dim coarse cells of size H; those for which
+    refine(i,j,k) is true are split into 2^dim children (hanging faces towards coarse neighbours).
+    Cells are numbered along the Morton curve of their lower corner on the fine lattice; one interface
+    per pair of face neighbours, sized by the finer side, OWNER = THE FINER CELL (else the low-side
+    cell), normal from owner to neighbour (so interior normals of both signs occur); interfaces are
+    created cell by cell in the order -x,+x,-y,+y,(-z,+z). Test-side generator, small sizes only."""
+    nz0 = n0 if dim == 3 else 1
+    nf = 2 * n0                                             # fine lattice cells per side
+    nfz = 2 * nz0 if dim == 3 else 1
+    h = 0.5 * H
+
+    def morton(i, j, k):
+        key = 0
+        for b in range(16):
+            key |= ((i >> b) & 1) << (3 * b) | ((j >> b) & 1) << (3 * b + 1) | ((k >> b) & 1) << (3 * b + 2)
+        return key
+
+    cells = []                                              # (morton key, fine i, j, k, level)
+    for k0 in range(nz0):
+        for j0 in range(n0):
+            for i0 in range(n0):
+                if refine(i0, j0, k0):
+                    for dk in range(2 if dim == 3 else 1):
+                        for dj in range(2):
+                            for di in range(2):
+                                i, j, k = 2 * i0 + di, 2 * j0 + dj, (2 * k0 + dk) if dim == 3 else 0
+                                cells.append((morton(i, j, k), i, j, k, 1))
+                else:
+                    i, j, k = 2 * i0, 2 * j0, (2 * k0) if dim == 3 else 0
+                    cells.append((morton(i, j, k), i, j, k, 0))
+    cells.sort()
+    nc = len(cells)
+    lattice = -np.ones((nfz, nf, nf), np.int64)             # fine lattice -> cell id
+    for c, (_, i, j, k, lev) in enumerate(cells):
+        w = 1 if lev else 2
+        wz = w if dim == 3 else 1
+        lattice[k:k + wz, j:j + w, i:i + w] = c
+    assert (lattice >= 0).all()
+
+    size = np.array([h if lev else H for (_, _, _, _, lev) in cells])
+    cc = np.empty((nc, 3))
+    for c, (_, i, j, k, lev) in enumerate(cells):
+        w = size[c]
+        cc[c] = (origin[0] + i * h + 0.5 * w, origin[1] + j * h + 0.5 * w,
+                 (origin[2] + k * h + 0.5 * w) if dim == 3 else origin[2])
+    owner, neigh, normal, area, bc, icent = [], [], [], [], [], []
+    seen = set()
+    ext = (nf, nf, nfz)
+    for c, (_, i, j, k, lev) in enumerate(cells):
+        w = 1 if lev else 2
+        lo = (i, j, k)
+        for face in range(2 * dim):
+            d, sgn = face // 2, (1 if face % 2 else -1)
+            q = lo[d] + (w if sgn > 0 else -1)              # fine-lattice coordinate just across the face
+            n = [0.0, 0.0, 0.0]
+            n[d] = float(sgn)
+            t_axes = [a for a in range(dim) if a != d]
+            if q < 0 or q >= ext[d]:
+                fc = list(cc[c]); fc[d] += sgn * 0.5 * size[c]
+                owner.append(c); neigh.append(-1); normal.append(n); area.append(size[c] ** (dim - 1))
+                bc.append(bc_code); icent.append(fc)
+                continue
+            # distinct neighbours across this face (1, or 2^(dim-1) finer ones)
+            nbs = []
+            for s1 in range(w):
+                for s2 in range(w if dim == 3 else 1):
+                    p = list(lo)
+                    p[d] = q
+                    p[t_axes[0]] += s1
+                    if dim == 3:
+                        p[t_axes[1]] += s2
+                    nb = int(lattice[p[2], p[1], p[0]])
+                    if nb not in nbs:
+                        nbs.append(nb)
+            for nb in nbs:
+                pair = (min(c, nb), max(c, nb), d)
+                if pair in seen:
+                    continue
+                seen.add(pair)
+                fs = min(size[c], size[nb])
+                finer = c if size[c] < size[nb] else (nb if size[nb] < size[c] else (c if sgn > 0 else nb))
+                other = nb if finer == c else c
+                nn = [0.0, 0.0, 0.0]
+                nn[d] = float(sgn) if finer == c else float(-sgn)
+                fc = list(cc[finer]); fc[d] += nn[d] * 0.5 * fs
+                owner.append(finer); neigh.append(other); normal.append(nn); area.append(fs ** (dim - 1))
+                bc.append(-1); icent.append(fc)
+    nfaces = len(owner)
+    return dict(dim=dim, owner=np.array(owner, np.int64), neigh=np.array(neigh, np.int64),
+                bc=np.array(bc, np.int32), area=np.array(area), normal=np.array(normal),
+                icentroid=np.array(icent), volume=size ** dim, size=size, ccentroid=cc,
+                solved=np.ones(nc, np.uint8), internal=np.ones(nc, np.uint8), fluid=np.ones(nc, np.uint8),
+                h=float(size.min()), n_faces=nfaces)

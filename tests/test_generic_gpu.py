@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff
+from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff, two_level_mesh
 
 pytestmark = pytest.mark.gpu
 
@@ -123,6 +123,36 @@ def test_dirichlet_ffstep_bit_exact(mmf, oracle):
         eig = s.compute_rhs(mmf.FIELD_U)
         got = s.get_state(mmf.FIELD_RHS)
     assert eig == ref_eig and bits_equal(got, ref)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_hanging_faces_bit_exact(mmf, oracle, dim):
+    """Non-uniform (2:1) octree: coarse cells meet 2^(dim-1) interfaces on a refined side, interfaces
+    are owned by the finer cell so interior normals of both signs occur, and cell sizes differ (volume
+    in the RK update, min size in dt). Residual, stage updates and fused steps are bit-exact."""
+    m = two_level_mesh(dim, 6, lambda i, j, k: (1 <= i < 4 and 2 <= j < 5 and k < 3) or (i, j, k) == (5, 5, 0) or (i + j + k) % 5 == 0)
+    m["problem"] = "radsod"
+    nc = m["volume"].shape[0]
+    rng = np.random.default_rng(11)
+    rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-0.4, 0.4, (nc, 3)); p = rng.uniform(0.6, 1.4, nc)
+    if dim == 2:
+        vel[:, 2] = 0.0
+    U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+    ref, ref_eig = oracle.compute_rhs(m, U)
+    with _solver(mmf, m) as s:
+        assert s.info()["path"] == mmf.PATH_GENERIC
+        s.set_state(mmf.FIELD_U, U)
+        eig = s.compute_rhs(mmf.FIELD_U)
+        got = s.get_state(mmf.FIELD_RHS)
+        assert eig == ref_eig and bits_equal(got, ref)
+        Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+        t = 0.0
+        for _ in range(6):
+            dt, me3 = oracle.step(m, 0.45, t, 10.0, Uo, Wo, Ro)
+            dtg, meg = s.step(0.45, m["h"], t, 10.0)
+            assert dtg == dt and list(me3) == meg
+            t += dt
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
 
 
 def test_rk_stages_and_step_bit_exact(mmf, oracle):

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import bits_equal, lexicographic_box_mesh
+from common import bits_equal, lexicographic_box_mesh, two_level_mesh
 from oracle_lib import PROBLEMS
 
 _D = C.POINTER(C.c_double)
@@ -136,3 +136,37 @@ def test_lexicographic_generator_matches_morton_physics(oracle):
     R1, e1 = oracle.compute_rhs(m, U)
     R2, e2 = oracle.compute_rhs(lx, Ul)
     assert e1 == e2 and np.allclose(R2[perm], R1, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_two_level_mesh_freestream_and_conservation(oracle, dim):
+    """Hanging (2:1) faces: the face loop (src/euler.cpp:150-245) is connectivity-driven, so a coarse
+    cell simply meets 2^(dim-1) interfaces on a refined side. Free stream stays free stream and, with
+    reflecting borders, the residuals of mass and energy sum to rounding (every interior flux enters
+    two cells with opposite signs; the mirror state gives exactly zero mass/energy flux)."""
+    m = two_level_mesh(dim, 4, lambda i, j, k: (i in (1, 2) and j in (1, 2) and k in (0, 1, 2)) or (i, j, k) == (3, 3, 0))
+    m["problem"] = "radsod"
+    nc = m["volume"].shape[0]
+    inter = m["neigh"] >= 0
+    assert (m["size"][m["owner"][inter]] != m["size"][np.maximum(m["neigh"], 0)[inter]]).any()
+    assert np.isclose(m["volume"].sum(), 4.0 ** dim)
+    # closed cells: sum of A*n over the faces of every cell vanishes exactly (power-of-two sizes)
+    acc = np.zeros((nc, 3))
+    np.add.at(acc, m["owner"], m["area"][:, None] * m["normal"])
+    np.add.at(acc, m["neigh"][inter], -(m["area"][:, None] * m["normal"])[inter])
+    assert np.all(acc == 0.0)
+    # free stream (free-flow borders)
+    ff = dict(m, bc=np.where(inter, -1, 0).astype(np.int32))
+    vel = (0.3, -0.2, 0.1 if dim == 3 else 0.0)
+    U = np.tile([1.0, vel[0], vel[1], vel[2], 1.0 / 0.4 + 0.5 * sum(v * v for v in vel)], (nc, 1))
+    R, me = oracle.compute_rhs(ff, U)
+    assert np.abs(R).max() < 1e-13 and me > 0
+    # conservation with reflecting borders
+    rng = np.random.default_rng(5)
+    U = _random_states(rng, nc)
+    if dim == 2:
+        U[:, 4] -= 0.5 * U[:, 3] ** 2 / U[:, 0]
+        U[:, 3] = 0.0
+    R, _ = oracle.compute_rhs(m, U)
+    scale = np.abs(R).max()
+    assert abs(R[:, 0].sum()) < 1e-12 * scale * nc and abs(R[:, 4].sum()) < 1e-12 * scale * nc
