@@ -46,20 +46,6 @@ __device__ __forceinline__ int order_key(int coord, int axis)
     return (ORDER == NUM_LEXI) ? axis : 3 * (__ffs(coord) - 1) + axis;
 }
 
-__device__ __forceinline__ float rcp_approx_f32(float x)
-{
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ float sqrt_approx_f32(float x)
-{
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // FP32 ESTIMATE of a cell's largest side eigenvalue max_d |u_d| + a (src/euler.cpp:59-66).  Stage 3
 // evaluates it for the state it writes and keeps the maximum per CTA; the next step's exact max
 // eigenvalue (src/main.cpp:398) is then found by re-evaluating in FP64 only the tiles whose estimate

@@ -1,0 +1,51 @@
+// tools/emu/emu_ptx_helpers.h -- CPU stand-ins for minimmerflow_b200/csrc/ptx_helpers.cuh
+// (DEVELOPMENT TOOL, see shim/cuda_runtime.h).
+//
+//  * mbarrier: one 64-bit word, [phase : 32 | expected : 16 | pending : 16], with the PTX semantics the
+//    kernels rely on: an arrival decrements `pending`, the last one starts the next phase;
+//    try_wait.parity(P) succeeds once the CURRENT phase's parity differs from P.  A waiter that is
+//    overtaken by two phase completions therefore never wakes up -- on the GPU and here.
+//  * division: on the GPU a/b == div_nr(a, b, rcp_nr(b)) bit for bit (mmf_selftest_division checks
+//    that on the device); the reciprocal seed instruction does not exist on the CPU, so here div_nr IS
+//    the IEEE division.  The emulator checks protocol and indexing, not that identity.
+//  * the approximate FP32 operations only feed the eigenvalue ESTIMATE (never compared bitwise).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace mmf {
+
+inline void mbar_init(unsigned long long *bar, unsigned count)
+{
+    __atomic_store_n(bar, ((unsigned long long) count << 16) | count, __ATOMIC_SEQ_CST);
+}
+
+inline void mbar_arrive(unsigned long long *bar)
+{
+    emu::chaos_delay();
+    unsigned long long old = __atomic_load_n(bar, __ATOMIC_RELAXED), upd;
+    do {
+        const unsigned long long phase = old >> 32, expected = (old >> 16) & 0xffffu, pending = old & 0xffffu;
+        if (pending == 0) { fprintf(stderr, "emu: arrival on an uninitialised mbarrier\n"); abort(); }
+        upd = (pending == 1) ? (((phase + 1) << 32) | (expected << 16) | expected)
+                             : ((phase << 32) | (expected << 16) | (pending - 1));
+    } while (!__atomic_compare_exchange_n(bar, &old, upd, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED));
+}
+
+inline void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    emu::chaos_delay();
+    long long spins = 0;
+    while (((__atomic_load_n(bar, __ATOMIC_ACQUIRE) >> 32) & 1u) == (parity & 1u)) {
+        emu::yield_lane();
+        emu::spin_pause(spins, "mbar_wait");
+    }
+}
+
+inline double rcp_nr(double b) { return 1.0 / b; }
+inline double div_nr(double a, double b, double) { return a / b; }
+
+inline float rcp_approx_f32(float x) { return 1.0f / x; }
+inline float sqrt_approx_f32(float x) { return sqrtf(x); }
+
+} // namespace mmf

@@ -1,0 +1,283 @@
+// tools/emu/emu_stage.cpp -- DEVELOPMENT TOOL (see shim/cuda_runtime.h): the fiber runtime and a C entry
+// point that runs ONE launch of a fused stage kernel, compiled from the product's kernel source, on padded
+// host arrays.  tools/emu/run_emu.py drives it and compares with the CPU oracle.
+#include <cuda_runtime.h>
+
+#include <sys/mman.h>
+
+#include <functional>
+#include <thread>
+#include <vector>
+
+// ---- runtime --------------------------------------------------------------------------------------
+namespace emu {
+
+thread_local Lane *tl_cur = nullptr;
+uint3e g_blockIdx, g_blockDim, g_gridDim;
+int g_chaos = 0;
+long long g_spin_limit = 20000000;
+
+struct Cta {
+    int n_threads = 0;
+    std::atomic<int> bar_count{0};
+    std::atomic<unsigned> bar_gen{0};
+    std::function<void()> body;
+};
+
+void yield_lane()
+{
+    Lane *me = tl_cur;
+    Warp *w = me->warp;
+    for (int d = 1; d < 32; ++d) {
+        Lane *n = &w->lanes[(me->lane + d) & 31];
+        if (!n->done) {
+            tl_cur = n;
+            swapcontext(&me->ctx, &n->ctx);
+            return;
+        }
+    }
+}
+
+void spin_pause(long long &spins, const char *what)
+{
+    ++spins;
+    if ((spins & 63) == 0) sched_yield();
+    if (spins > g_spin_limit) {
+        Lane *me = tl_cur;
+        fprintf(stderr, "emu: HANG in %s: block (%u,%u,%u) warp %d lane %d gave up after %lld yields\n", what,
+                g_blockIdx.x, g_blockIdx.y, g_blockIdx.z, me->warp->index, me->lane, spins);
+        fflush(stderr);
+        _exit(3);
+    }
+}
+
+void chaos_delay()
+{
+    if (g_chaos <= 0) return;
+    Warp *w = tl_cur->warp;
+    w->rng = w->rng * 1664525u + 1013904223u;
+    const unsigned r = w->rng >> 8;
+    if (r % 16 == 0) usleep(r % (unsigned) g_chaos);
+    else if (r % 4 == 0) sched_yield();
+}
+
+void cta_barrier()
+{
+    Cta *c = tl_cur->warp->cta;
+    const unsigned g = c->bar_gen.load();
+    if (c->bar_count.fetch_add(1) + 1 == c->n_threads) {
+        c->bar_count.store(0);
+        c->bar_gen.fetch_add(1);
+    } else {
+        long long spins = 0;
+        while (c->bar_gen.load() == g) { yield_lane(); spin_pause(spins, "__syncthreads"); }
+    }
+}
+
+static void lane_entry()
+{
+    Lane *me = tl_cur;
+    me->warp->cta->body();
+    me->done = true;
+    Warp *w = me->warp;
+    for (int d = 1; d < 32; ++d) {
+        Lane *n = &w->lanes[(me->lane + d) & 31];
+        if (!n->done) { tl_cur = n; setcontext(&n->ctx); }
+    }
+    // last lane of the warp: returning resumes uc_link = the warp's main context
+}
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+static void warp_main(Warp *w, char *stacks)
+{
+    for (int l = 0; l < 32; ++l) {
+        Lane &L = w->lanes[l];
+        getcontext(&L.ctx);
+        L.ctx.uc_stack.ss_sp = stacks + (size_t) l * STACK_BYTES;
+        L.ctx.uc_stack.ss_size = STACK_BYTES;
+        L.ctx.uc_link = &w->main;
+        makecontext(&L.ctx, lane_entry, 0);
+    }
+    tl_cur = &w->lanes[0];
+    swapcontext(&w->main, &w->lanes[0].ctx);
+    for (int l = 0; l < 32; ++l) {
+        if (!w->lanes[l].done) { fprintf(stderr, "emu: warp %d ended with lane %d unfinished\n", w->index, l); _exit(4); }
+    }
+}
+
+// runs the CTAs of a grid one after the other; `body` is the kernel call with its arguments bound
+static void launch(unsigned gx, unsigned gy, unsigned gz, int n_threads, void *smem, size_t smem_bytes,
+                   const std::function<void()> &body, unsigned seed)
+{
+    const int nw = n_threads / 32;
+    static char *stacks = nullptr;
+    static size_t stacks_bytes = 0;
+    const size_t need = (size_t) nw * 32 * STACK_BYTES;
+    if (need > stacks_bytes) {
+        if (stacks) munmap(stacks, stacks_bytes);
+        stacks = (char *) mmap(nullptr, need, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (stacks == MAP_FAILED) { perror("mmap"); _exit(5); }
+        stacks_bytes = need;
+    }
+    g_gridDim = { gx, gy, gz };
+    g_blockDim = { (unsigned) n_threads, 1, 1 };
+    std::vector<Warp> warps((size_t) nw);
+    for (unsigned bz = 0; bz < gz; ++bz)
+        for (unsigned by = 0; by < gy; ++by)
+            for (unsigned bx = 0; bx < gx; ++bx) {
+                g_blockIdx = { bx, by, bz };
+                memset(smem, 0xff, smem_bytes); // shared memory starts as NaNs: reads of unwritten slots show up
+                Cta cta;
+                cta.n_threads = n_threads;
+                cta.body = body;
+                for (int wi = 0; wi < nw; ++wi) {
+                    Warp &w = warps[wi];
+                    memset(w.arrived, 0, sizeof w.arrived);
+                    memset(w.departed, 0, sizeof w.departed);
+                    w.cta = &cta;
+                    w.index = wi;
+                    w.rng = seed * 2654435761u + (unsigned) wi * 40503u + bx * 7919u + by * 104729u + bz * 1299709u;
+                    for (int l = 0; l < 32; ++l) {
+                        Lane &L = w.lanes[l];
+                        L.tid = { (unsigned) (wi * 32 + l), 0, 0 };
+                        L.warp = &w;
+                        L.lane = l;
+                        L.gen = 0;
+                        L.done = false;
+                    }
+                }
+                std::vector<std::thread> threads;
+                for (int wi = 0; wi < nw; ++wi) threads.emplace_back(warp_main, &warps[wi], stacks + (size_t) wi * 32 * STACK_BYTES);
+                for (auto &t : threads) t.join();
+            }
+}
+
+} // namespace emu
+
+// ---- the product's kernel source --------------------------------------------------------------------
+namespace mmf {
+alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double smem[]` (320 KB: room for variants)
+}
+
+#include "uniform_stage_v5r.cuh"
+#ifdef MMF_EMU_HAVE_V6
+#include "uniform_stage_v6.cuh"
+#endif
+
+namespace {
+
+using namespace mmf;
+
+struct Args {
+    UniformGeom g;
+    const double *Sin, *Un;
+    double *Out;
+    StepControl *ctl;
+    double *max_eig;
+    int lz;
+    float *cta_est;
+    LoadClamp lc;
+    HaloWait hw;
+    XGhost xg;
+};
+
+template <int STAGE, int ORDER, int NW>
+std::function<void()> bind_kernel(int form, const Args &a)
+{
+    switch (form) {
+    case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+#ifdef MMF_EMU_HAVE_V6
+    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+#endif
+    default: return nullptr;
+    }
+}
+
+template <int STAGE, int ORDER>
+std::function<void()> bind_nw(int form, int nw, const Args &a)
+{
+    switch (nw) {
+    case 8:  return bind_kernel<STAGE, ORDER, 8>(form, a);
+    case 12: return bind_kernel<STAGE, ORDER, 12>(form, a);
+    case 16: return bind_kernel<STAGE, ORDER, 16>(form, a);
+    default: return nullptr;
+    }
+}
+
+template <int STAGE>
+std::function<void()> bind_order(int order, int form, int nw, const Args &a)
+{
+    switch (order) {
+    case NUM_MORTON: return bind_nw<STAGE, NUM_MORTON>(form, nw, a);
+    case NUM_LEXI:   return bind_nw<STAGE, NUM_LEXI>(form, nw, a);
+    case NUM_AXIS:   return bind_nw<STAGE, NUM_AXIS>(form, nw, a);
+    default: return nullptr;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// padded extents of a box, as uniform_alloc (uniform_path.cuh) lays them out
+void emu_padded(const int dims[3], int pad[3], long long *fs)
+{
+    pad[0] = (dims[0] + 2 + 3) / 4 * 4;
+    pad[1] = dims[1] + 2;
+    pad[2] = dims[2] + 2;
+    *fs = ((long long) pad[0] * pad[1] * pad[2] + 15) / 16 * 16;
+}
+
+// One launch of a fused stage kernel.  Arrays are padded SoA [field][k+1][j+1][i+1] as on the device.
+// smem_doubles: dynamic shared memory the host side would request for this form (checked against the
+// tool's static array).  Returns 0, or a negative code for an unknown configuration.
+int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3], const int goff[3], const int gdims[3],
+              const int bc[6], double h, double area, double volume, const double dirichlet[5], const int clamp[6],
+              const double *Sin, const double *Un, double *Out, double dt, double *max_eig, float *cta_est,
+              int smem_doubles, int chaos, unsigned seed)
+{
+    Args a{};
+    UniformGeom &g = a.g;
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    g.gx0 = goff[0]; g.gy0 = goff[1]; g.gz0 = goff[2];
+    g.gnx = gdims[0]; g.gny = gdims[1]; g.gnz = gdims[2];
+    int pad[3];
+    emu_padded(dims, pad, &g.fs);
+    g.px = pad[0]; g.py = pad[1]; g.pz = pad[2];
+    g.h = h; g.area = area; g.volume = volume;
+    for (int s = 0; s < 6; ++s) g.bc[s] = bc[s];
+    for (int k = 0; k < NF; ++k) g.dirichlet[k] = dirichlet[k];
+    a.lc = { clamp[0], clamp[1], clamp[2], clamp[3], clamp[4], clamp[5] };
+    StepControl ctl{};
+    ctl.dt = dt;
+    ctl.active = 1.0;
+    a.ctl = &ctl;
+    a.Sin = Sin; a.Un = Un; a.Out = Out;
+    a.max_eig = max_eig;
+    a.lz = lz;
+    a.cta_est = cta_est;
+    const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + (nw - 2) - 1) / (nw - 2), gz = (g.nz + lz - 1) / lz;
+    a.hw = HaloWait{};
+    a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;
+    a.xg = XGhost{};
+    if ((size_t) smem_doubles * sizeof(double) > sizeof(mmf::smem)) return -2;
+
+    std::function<void()> body;
+    switch (stage) {
+    case 0: body = bind_order<0>(order, form, nw, a); break;
+    case 1: body = bind_order<1>(order, form, nw, a); break;
+    case 2: body = bind_order<2>(order, form, nw, a); break;
+    case 3: body = bind_order<3>(order, form, nw, a); break;
+    default: break;
+    }
+    if (!body) return -1;
+    emu::g_chaos = chaos;
+    emu::launch(gx, gy, gz, nw * 32, mmf::smem, (size_t) smem_doubles * sizeof(double), body, seed);
+    return 0;
+}
+
+void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }
+
+} // extern "C"
