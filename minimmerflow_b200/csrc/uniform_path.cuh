@@ -7,6 +7,7 @@
 #include "uniform_stage_v3.cuh"
 #include "uniform_stage_v5.cuh"
 #include "uniform_stage_v5r.cuh"
+#include "uniform_stage_v6.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -18,7 +19,9 @@ namespace mmf {
 
 // which stage-kernel form runs a stage and with how many warps per CTA:
 //   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
-//   '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check
+//   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
+//       has been measured on the GPU), '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps),
+//       kept as an independent cross-check
 struct StageShape {
     char form = 'p';
     int nw = 16;
@@ -184,14 +187,13 @@ static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, c
 }
 
 template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, const double *Sin, const double *Un, double *Out, double *d_max)
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
+                          double *d_max)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
     const int lz = u->shape[stage].lz;
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
-    // record (11) + flux (5) doubles per lane and row, two mbarriers per row
-    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     for (int q = 0; q < 3; ++q) {
         if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
@@ -237,7 +239,16 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     const StageShape sh = u->shape[STAGE];
     if (sh.form == '3') return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
     const bool xgk = uniform_use_xghost(ctx);
-#define MMF_LAUNCH(KERN, NWV, XGV) return launch_stage_k(ctx, KERN<STAGE, ORDER, NWV, XGV>, STAGE, NWV, Sin, Un, Out, d_max)
+    // v5 forms: record (11) + flux (5) doubles per lane and row, two mbarriers per row; v6: twice that
+#define MMF_SMEM_V5(NWV) ((size_t) (NWV) * 16 * 32 * sizeof(double) + 2 * (NWV) * sizeof(unsigned long long))
+#define MMF_LAUNCH6(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v6<STAGE, ORDER, NWV, XGV>, STAGE, NWV, stage_v6_smem_bytes(NWV), Sin, Un, Out, d_max)
+#define MMF_LAUNCH(KERN, NWV, XGV) return launch_stage_k(ctx, KERN<STAGE, ORDER, NWV, XGV>, STAGE, NWV, MMF_SMEM_V5(NWV), Sin, Un, Out, d_max)
+    if (sh.form == 'd') {
+        if (sh.nw == 16) { if (xgk) MMF_LAUNCH6(16, true); MMF_LAUNCH6(16, false); }
+        if (sh.nw == 8) MMF_LAUNCH6(8, false);
+        if (xgk) MMF_LAUNCH6(12, true);
+        MMF_LAUNCH6(12, false);
+    }
     if (sh.form == 'r') {
         if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5r, 16, false); }
         if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5r, 8, false);
@@ -249,6 +260,8 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 12, true);
     MMF_LAUNCH(uniform_stage_kernel_v5, 12, false);
 #undef MMF_LAUNCH
+#undef MMF_LAUNCH6
+#undef MMF_SMEM_V5
 }
 
 template <int STAGE>
@@ -303,7 +316,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // Launch shapes, measured at 256^3 on B200 (profiles/): the ping-pong form at 16 warps (128
     // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (164-166
     // registers, no spills) the fastest for stages 2 and 3, which also stream U^n.
-    // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "312" = v3 everywhere.
+    // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "d12" = the decoupled form
+    // everywhere, "312" = v3 everywhere.
     const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
     for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
@@ -315,7 +329,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages

@@ -1,0 +1,391 @@
+// uniform_stage_v6.cuh -- the low-face streaming stage kernel (uniform_stage_v5.cuh explains the scheme)
+// with the y exchange DECOUPLED by one plane.
+//
+// In v5 a row publishes its record (U, Fy, lam_y) of plane k, the row above turns it into the low y flux
+// of its own cell and publishes that, and the first row waits for it IN THE SAME PLANE to subtract it as
+// its -y_hi: record(r,k) -> flux(r+1,k) -> S(r,k).  That round trip ties every row to both neighbours
+// within a plane, so the rows of a CTA move in lock step and any delay of one warp (a DRAM load, a lost
+// issue slot) is handed to all of them: profiles/r01d shows 22-30 % of the warp time in those waits.
+//
+// Here -y_hi is subtracted ONE PLANE LATER, together with -z_hi which has to wait for the next plane
+// anyway (both are the last two terms of the reference's accumulation order, src/euler.cpp:237-247, so
+// the order of operations per value is unchanged and the result stays bit-identical):
+//   iteration k of row r:  publish record(r,k) | z face (k-1|k)
+//                          | wait flux(r+1,k-1): S(k-1) -= it; S(k-1) -= AFz; update + store plane k-1
+//                          | x face | wait record(r-1,k) -> y face, publish flux(r,k)
+//                          | S(k) = ordered low faces - x_hi (+ y_lo on the border)
+// The only same-plane dependency left points downwards (record of row r-1), so the rows settle into a
+// skew instead of a lock step, and the flux a row waits for was published about one plane earlier.
+// Records and fluxes are double buffered (slot = plane parity) with one mbarrier per slot and row: with a
+// single barrier the producer could complete two phases before the consumer's parity wait looks at the
+// first one (try_wait.parity cannot tell phase k from phase k+2), which is a hang.  Why no slot is
+// overwritten early and no barrier is overtaken is argued next to each wait below; tools/emu runs this
+// source on a CPU SIMT emulator with the same mbarrier semantics and random warp delays to check it.
+//
+// Two situations keep the same-plane wait: the plane on the low z side of the DOMAIN, whose border face
+// enters the sum after -y_hi (one plane of one z chunk), and the NUM_AXIS accumulation order
+// (x_lo - x_hi + y_lo - y_hi + z_lo - z_hi for every cell).
+#pragma once
+
+#include "uniform_stage_v5r.cuh"
+
+#include <type_traits>
+
+namespace mmf {
+
+// dynamic shared memory of the v6 kernels: records (11) + fluxes (5) doubles per lane, row and slot,
+// four mbarriers per row
+__host__ __device__ constexpr size_t stage_v6_smem_bytes(int nw)
+{
+    return (size_t) 2 * nw * 16 * 32 * sizeof(double) + (size_t) 4 * nw * sizeof(unsigned long long);
+}
+
+// The plane loop, two planes per trip with the slot (= plane parity) a compile-time constant in each
+// copy of the body, so that slot offsets fold into the shared-memory addresses.
+#define MMF_V6_PLANE_PAIRS(IT0, SLOT)                                                                        \
+    _Pragma("unroll 1") for (int IT0 = 0; IT0 < z1 - z0; IT0 += 2)                                          \
+        _Pragma("unroll") for (int SLOT = 0; SLOT < 2; ++SLOT)                                              \
+            if (IT0 + SLOT < z1 - z0)
+
+template <int STAGE, int ORDER, int NW, bool XG>
+__global__ void __maxnreg__(stage_regs(NW))
+uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
+                        const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
+                        float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw, const XGhost xg)
+{
+    extern __shared__ double smem[];
+    // sm_d[slot][row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[slot][row][k][lane] = area * flux of (j-1 | j)
+    constexpr int DS = NW * 11 * 32, FS = NW * NF * 32; // doubles per slot
+    double *sm_d = smem;
+    double *sm_f = smem + 2 * DS;
+    unsigned long long *barD = reinterpret_cast<unsigned long long *>(sm_f + 2 * FS); // [slot][row]: record published
+    unsigned long long *barF = barD + 2 * NW;                                          // [slot][row]: low y flux published
+
+    if (STAGE >= 1 && ctl->active == 0.0) return;
+
+    const int lane = threadIdx.x & 31;
+    const int row  = threadIdx.x >> 5;
+    const TileId tid = stage_tile(hw);
+    if (threadIdx.x < 2 * NW) {
+        mbar_init(&barD[threadIdx.x], 1);
+        mbar_init(&barF[threadIdx.x], 1);
+    }
+    halo_wait(hw, tid);
+    __syncthreads();
+
+    const int i  = tid.bx * XW - 1 + lane;
+    const int j  = tid.by * (NW - 2) - 1 + row;
+    const int z0 = tid.bz * lz;
+    const int z1 = min(z0 + lz, g.nz);
+    const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
+    const int jc = min(max(j, lc.jlo), lc.jhi);
+    const bool in_x = (i >= 0 && i < g.nx);
+    const bool in_y = (j >= 0 && j < g.ny);
+
+    const double Ah = 0.5 * g.area;
+    DivConsts dc;
+    dc.y_gm1 = rcp_nr(GM1);
+    dc.y_c1  = rcp_nr(TWO_OVER_GM1);
+    dc.y_vol = rcp_nr(g.volume);
+
+    const long long plane = (long long) g.py * g.px;
+    const long long fs    = g.fs;
+    const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
+    const double *scol = Sin + col;
+    int sfs_lane = (int) fs, splane_lane = (int) plane; // element counts: < 2^31 for any box that fits one GPU
+    if (XG) {
+        if (xg.lo && i < 0)     { scol = xg.lo + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+        if (xg.hi && i >= g.nx) { scol = xg.hi + (jc + 1); sfs_lane = (int) xg.fs; splane_lane = xg.pitch; }
+    }
+    const long long sfs = XG ? (long long) sfs_lane : fs, splane = XG ? (long long) splane_lane : plane;
+    double lmax = 0.0;
+    float emax = 0.f;
+
+    if (row == 0) {
+        // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
+        double nxt[NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+        MMF_V6_PLANE_PAIRS(it0, slot) {
+            const int it = it0 + slot, kz = z0 + it;
+            double *d = sm_d + slot * DS + lane;
+            double cU[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
+            sp += splane;
+            if (kz + 1 < z1) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+            }
+            CellPrim q;
+            derive_cell(cU, dc, q);
+            double cFy[NF], cly;
+            axis_flux<1>(q, cFy, cly);
+            // the slot still holds record it-2: row 1 has read it once its flux it-2 is out.  Row 1 cannot
+            // complete this barrier again before it has seen record `it`, which follows this wait.
+            if (it >= 2) mbar_wait(&barF[slot * NW + 1], (unsigned) (((it - 2) >> 1) & 1));
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { d[k * 32] = cU[k]; d[(NF + k) * 32] = cFy[k]; }
+            d[10 * 32] = cly;
+            mbar_arrive_elect(&barD[slot * NW + 0], lane);
+        }
+    } else if (row == NW - 1) {
+        // ================= high halo row: computes the y face (j-1 | j) for row NW-2 ================
+        const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;
+        const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
+        double lmy = 0.0;
+        double nxt[NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+        MMF_V6_PLANE_PAIRS(it0, slot) {
+            const int it = it0 + slot, kz = z0 + it;
+            const double *d_dn = sm_d + slot * DS + (NW - 2) * 11 * 32 + lane;
+            double *f = sm_f + slot * FS + (NW - 1) * NF * 32 + lane;
+            double cU[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
+            sp += splane;
+            if (kz + 1 < z1) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+            }
+            CellPrim q;
+            derive_cell(cU, dc, q);
+            double cFy[NF], cly;
+            axis_flux<1>(q, cFy, cly);
+            // row NW-2 publishes record it+2 on this barrier only after it has taken flux `it`, below
+            mbar_wait(&barD[slot * NW + NW - 2], (unsigned) ((it >> 1) & 1));
+            double lU[NF], lF[NF], AFy[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
+            const double ll  = d_dn[10 * 32];
+            const double lam = llf_area_flux(lU, lF, ll, cU, cFy, cly, Ah, AFy);
+            lmy = (lam < lmy) ? lmy : lam;
+            // the slot held flux it-2: row NW-2 took it during its plane it-1, before it published record `it`
+#pragma unroll
+            for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
+            mbar_arrive_elect(&barF[slot * NW + NW - 1], lane);
+        }
+        lmax = yf_ok ? lmy : 0.0;
+    } else {
+        // ================= update rows ==============================================================
+        const bool upd   = lane >= 1 && lane <= XW && in_x && in_y;
+        const bool xf_ok = in_y && lane >= 1 && i >= 0 && i <= g.nx;                  // face (i-1 | i)
+        const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;   // face (j-1 | j)
+        const bool zf_ok = in_x && in_y;                                              // face (k-1 | k)
+        const double dt = (STAGE >= 1) ? ctl->dt : 0.0;
+        const int key_x = order_key<ORDER>(g.gx0 + i, 0);
+        const int key_y = order_key<ORDER>(g.gy0 + j, 1);
+        float est_max = 0.f;
+
+        double *d_own = sm_d + row * 11 * 32 + lane;             // + slot * DS
+        const double *d_dn = sm_d + (row - 1) * 11 * 32 + lane;
+        double *f_own = sm_f + row * NF * 32 + lane;             // + slot * FS
+        const double *f_up = sm_f + (row + 1) * NF * 32 + lane;
+
+        const double *sp  = scol + (long long) (max(z0 - 1, lc.klo) + 1) * splane; // plane z0-1 (clamped)
+        const double *unp = Un + col + (long long) (z0 + 1) * plane; // plane z0
+        double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
+
+        double pU[NF], pFz[NF], plz, pS[NF], pUn[NF], nxt[NF];
+        double lmx = 0.0, lmy = 0.0, lmz = 0.0;
+        // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
+        {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) pU[k] = ldsin(sp + k * sfs);
+            sp = scol + (long long) (z0 + 1) * splane; // plane z0
+#pragma unroll
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+            CellPrim q;
+            derive_cell(pU, dc, q);
+            axis_flux<2>(q, pFz, plz);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { pS[k] = 0.0; pUn[k] = 0.0; }
+        }
+
+        // one plane; the slot (= plane parity) arrives as a compile-time constant so that the slot offsets
+        // fold into the shared-memory addresses
+        auto body = [&](auto slot_tag, const int it) {
+            constexpr int slot = decltype(slot_tag)::value;
+            const int kz = z0 + it;
+            const unsigned par = (unsigned) ((it >> 1) & 1);
+            double cU[NF];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) cU[k] = nxt[k];
+            if (kz + 1 <= lc.khi) sp += splane; // plane kz+1 (the ghost plane nz, or plane nz-1 again on a free-flow side)
+#pragma unroll
+            for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
+            double cUn[NF];
+            if (STAGE >= 2 && upd) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) cUn[k] = unp[k * fs];
+            }
+            unp += plane;
+
+            CellPrim q;
+            derive_cell(cU, dc, q);
+
+            // ---- y record for row+1.  The slot held record it-2; row+1 read it before it published flux
+            //      it-2, and this row took that flux during plane it-1 (or it-2): free. -------------------
+            double cFy[NF], cly;
+            axis_flux<1>(q, cFy, cly);
+            {
+                double *d = d_own + slot * DS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { d[k * 32] = cU[k]; d[(NF + k) * 32] = cFy[k]; }
+                d[10 * 32] = cly;
+            }
+            mbar_arrive_elect(&barD[slot * NW + row], lane);
+
+            // ---- z interface (kz-1 | kz) ---------------------------------------------------------------
+            double cFz[NF], clz, AFz[NF];
+            axis_flux<2>(q, cFz, clz);
+            {
+                const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
+                lmz = (lam < lmz) ? lmz : lam;
+            }
+            // ---- plane kz-1: -y_hi (the low y face of row+1, published one plane ago), -z_hi, update ----
+            // row+1 completes this barrier again (flux it+1) only after it has seen record it+1 of this
+            // row, which is published in the next iteration, after this wait.
+            if (ORDER != NUM_AXIS && it > 0 && g.gz0 + kz - 1 != 0) {
+                mbar_wait(&barF[(slot ^ 1) * NW + row + 1], (unsigned) (((it - 1) >> 1) & 1));
+                const double *f = f_up + (slot ^ 1) * FS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];
+            }
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
+            op += plane;
+
+            // ---- x interface (i-1 | i): lane-1's state by warp shuffle ---------------------------------
+            double AFx[NF];
+            {
+                double cFx[NF], clx, lU[NF], lF[NF];
+                axis_flux<0>(q, cFx, clx);
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { lU[k] = shfl_up_d(cU[k]); lF[k] = shfl_up_d(cFx[k]); }
+                const double ll  = shfl_up_d(clx);
+                const double lam = llf_area_flux(lU, lF, ll, cU, cFx, clx, Ah, AFx);
+                lmx = (lam < lmx) ? lmx : lam;
+            }
+
+            // ---- y interface (j-1 | j): row-1's record through shared memory --------------------------
+            // row-1 publishes record it+2 on this barrier only after it has taken this row's flux `it`
+            double AFy[NF];
+            mbar_wait(&barD[slot * NW + row - 1], par);
+            {
+                const double *d = d_dn + slot * DS;
+                double lU[NF], lF[NF];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { lU[k] = d[k * 32]; lF[k] = d[(NF + k) * 32]; }
+                const double ll  = d[10 * 32];
+                const double lam = llf_area_flux(lU, lF, ll, cU, cFy, cly, Ah, AFy);
+                lmy = (lam < lmy) ? lmy : lam;
+                // the slot held flux it-2: row-1 took it during its plane it-1, before it published the
+                // record `it` this row has just waited for
+                double *f = f_own + slot * FS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
+                mbar_arrive_elect(&barF[slot * NW + row], lane);
+            }
+
+            // ---- ordered accumulation (src/euler.cpp:153, 237-247) ------------------------------------
+            // interior low faces first, sorted by their creator (largest key first; a+b commutes, so
+            // only the LAST one matters); then the cell's own faces in the order it created them:
+            // (-x if border) +x (-y if border) +y (-z if border) +z; low faces `+=`, high faces `-=`.
+            // (plane kz-1 is finished: its registers take the sum of plane kz)
+            const int key_z = order_key<ORDER>(g.gz0 + kz, 2);
+            const bool edge = (key_y < 0) | (key_z < 0); // warp-uniform: one row, one plane per warp
+            if (ORDER == NUM_AXIS) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] = 0.0 + AFx[k];
+            } else if (!edge) {
+                // a border low face in x alone is simply "last" (key -1), directly followed by -x_hi
+                const int last = (key_x < key_y) ? ((key_x < key_z) ? 0 : 2) : ((key_y < key_z) ? 1 : 2);
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    const double p = (last == 0) ? AFy[k] : AFx[k];
+                    const double t = (last == 2) ? AFy[k] : AFz[k];
+                    const double r = (last == 0) ? AFx[k] : (last == 1) ? AFy[k] : AFz[k];
+                    pS[k] = (p + t) + r;
+                }
+            } else {
+                // low y / low z side of the domain: those faces enter after -x_hi, see below
+                const bool bx = key_x < 0;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    double s = 0.0; // at most two interior low faces remain: their order is immaterial
+                    if (!bx) s += AFx[k];
+                    if (key_y >= 0) s += AFy[k];
+                    if (key_z >= 0) s += AFz[k];
+                    if (bx) s += AFx[k];
+                    pS[k] = s;
+                }
+            }
+            // -x_hi: the low x face of lane+1
+#pragma unroll
+            for (int k = 0; k < NF; ++k) pS[k] -= shfl_down_d(AFx[k]);
+            if (ORDER == NUM_AXIS || (edge && key_y < 0)) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] += AFy[k];
+            }
+            // -y_hi follows one plane later, except where a +z_lo term has to come behind it
+            if (ORDER == NUM_AXIS || key_z < 0) {
+                mbar_wait(&barF[slot * NW + row + 1], par);
+                const double *f = f_up + slot * FS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] += AFz[k];
+            }
+
+            // ---- plane kz becomes the previous plane ---------------------------------------------------
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { pU[k] = cU[k]; pFz[k] = cFz[k]; }
+            plz = clz;
+            if (STAGE >= 2) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pUn[k] = cUn[k];
+            }
+        };
+        {
+            // two planes per trip, no test between them: ptxas renames the rotating state instead of copying it
+            const int n = z1 - z0;
+            int it = 0;
+#pragma unroll 1
+            for (; it + 1 < n; it += 2) {
+                body(std::integral_constant<int, 0>{}, it);
+                body(std::integral_constant<int, 1>{}, it + 1);
+            }
+            if (it < n) body(std::integral_constant<int, 0>{}, it);
+        }
+
+        // ---- epilogue: plane z1 only closes the last z interface; plane z1-1 still lacks -y_hi ------
+        {
+            CellPrim q;
+            derive_cell(nxt, dc, q);
+            double cFz[NF], clz, AFz[NF];
+            axis_flux<2>(q, cFz, clz);
+            const double lam = llf_area_flux(pU, pFz, plz, nxt, cFz, clz, Ah, AFz);
+            lmz = (lam < lmz) ? lmz : lam;
+            const int it = z1 - z0; // the iteration that would follow
+            if (ORDER != NUM_AXIS && g.gz0 + z1 - 1 != 0) {
+                mbar_wait(&barF[((it - 1) & 1) * NW + row + 1], (unsigned) (((it - 1) >> 1) & 1));
+                const double *f = f_up + ((it - 1) & 1) * FS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];
+            }
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
+        }
+        lmax = xf_ok ? lmx : 0.0;
+        if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;
+        if (zf_ok) lmax = (lmz < lmax) ? lmax : lmz;
+        emax = est_max;
+    }
+
+    block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, tid.tile, smem);
+}
+
+#undef MMF_V6_PLANE_PAIRS
+
+} // namespace mmf
