@@ -1,0 +1,67 @@
+"""The fused stage kernels' SOURCE, run on the CPU SIMT emulator of tools/emu (fibers per lane, PTX
+mbarrier phase/parity semantics, random warp delays) and compared with the oracle bit for bit.
+
+This is a check of the kernels' synchronisation protocol and index arithmetic -- a slot overwritten early,
+a barrier overtaken by two phases (a hang on the GPU), a ragged-tile slip -- that needs no GPU, so a new
+kernel form is debugged here before GPU minutes are spent on it.  It is NOT a product path (nothing in
+minimmerflow_b200/ can reach the emulator) and it proves nothing about SASS, registers or speed: the
+`-m gpu` tests through the C-ABI remain the parity proof."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
+
+import run_emu  # noqa: E402
+from common import lexicographic_box_mesh  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return run_emu.load()
+
+
+@pytest.mark.parametrize("form", ["p", "r", "d"])
+@pytest.mark.parametrize("chaos", [0, 300])
+def test_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, form, chaos):
+    # Morton cube (the reference's numbering), z chunks of 6 planes: general and steady-state bodies
+    m = oracle.problem_mesh("vortex_xy", 3, 16)
+    assert run_emu.check_case(emu, oracle, "vortex 16^3", dict(m), 0, form, 8, 6, 2, chaos, 1)
+    # ragged lexicographic box with reflecting borders (ghost pass), two-plane chunks, 12-warp CTAs
+    m = lexicographic_box_mesh(33, 8, 5, 0.5, 1)
+    assert run_emu.check_case(emu, oracle, "box 33x8x5", dict(m), 1, form, 12, 2, 1, chaos, 2)
+    # one-plane chunks on free-flow borders (clamped loads)
+    m = lexicographic_box_mesh(31, 7, 2, 0.5, 0)
+    assert run_emu.check_case(emu, oracle, "box 31x7x2", dict(m), 1, form, 8, 1, 1, chaos, 3)
+
+
+def test_emulated_mbarrier_keeps_ptx_phase_semantics(emu):
+    """The hazard the emulator exists to catch: a parity wait overtaken by two phase completions never
+    returns.  Checked on the barrier word itself (no kernel): after two completions the parity a waiter of
+    the first phase polls for is current again."""
+    import ctypes as C
+    emu.emu_mbar_selftest.restype = C.c_int
+    assert emu.emu_mbar_selftest() == 0
+
+
+def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
+    """NUM_AXIS accumulation (x_lo - x_hi + y_lo - y_hi + z_lo - z_hi) is not the reference's order, so
+    there is no oracle for its bits; the decoupled form keeps its same-plane wait there and must give
+    exactly what the rotate form gives, and both stay within rounding of the oracle."""
+    m = oracle.problem_mesh("radsod", 3, 16)
+    U0 = oracle.init_state(m)
+    ref, ref_eig = oracle.compute_rhs(m, U0)
+    out = {}
+    for form in ("r", "d"):
+        box = run_emu.Box(emu, oracle, dict(m), 2)
+        U, R = box.new_array(), box.new_array()
+        box.scatter(U, U0)
+        box.fill_ghosts(U)
+        eig, _ = box.stage(form, 0, 8, 5, U, U, R, 0.0, 200, 5)
+        assert eig == ref_eig
+        out[form] = box.gather(R)
+    assert np.array_equal(out["r"], out["d"])
+    assert np.abs(out["d"] - ref).max() <= 1e-13 * np.abs(ref).max()

@@ -280,4 +280,32 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
 
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }
 
+// phase bookkeeping of the emulated mbarrier word (no fibers involved: arrivals only, waits inspected)
+int emu_mbar_selftest()
+{
+    auto waiting = [](unsigned long long w, unsigned parity) { return ((w >> 32) & 1u) == (parity & 1u); };
+    unsigned long long bar = 0;
+    emu::Lane lane{};
+    emu::Warp warp{};
+    lane.warp = &warp;
+    emu::tl_cur = &lane; // chaos_delay() looks at the current lane's warp
+    const int chaos = emu::g_chaos;
+    emu::g_chaos = 0;
+    int bad = 0;
+    mmf::mbar_init(&bar, 2);
+    if (!waiting(bar, 0)) bad |= 1;          // phase 0 still running: a wait on parity 0 blocks
+    mmf::mbar_arrive(&bar);
+    if (!waiting(bar, 0)) bad |= 2;          // one of two arrivals: still blocked
+    mmf::mbar_arrive(&bar);
+    if (waiting(bar, 0)) bad |= 4;           // phase 0 complete: released
+    if (!waiting(bar, 1)) bad |= 8;          // phase 1 running
+    mmf::mbar_arrive(&bar);
+    mmf::mbar_arrive(&bar);
+    if (waiting(bar, 1)) bad |= 16;          // phase 1 complete
+    if (!waiting(bar, 0)) bad |= 32;         // ... and a late waiter of phase 0 would now block for good
+    emu::g_chaos = chaos;
+    emu::tl_cur = nullptr;
+    return bad;
+}
+
 } // extern "C"

@@ -220,6 +220,7 @@ def main():
         cases.append(("box 37x9x5 lexi free-flow", lexicographic_box_mesh(37, 9, 5, 0.25, 0), 1, 3))
         cases.append(("box 5x23x7 lexi reflecting", lexicographic_box_mesh(5, 23, 7, 0.5, 1), 1, 7))
         cases.append(("box 31x7x2 lexi free-flow", lexicographic_box_mesh(31, 7, 2, 0.5, 0), 1, 1))
+        cases.append(("box 33x8x5 lexi reflecting", lexicographic_box_mesh(33, 8, 5, 0.5, 1), 1, 2))
     all_ok = True
     for rep in range(args.repeat):
         for name, mesh, order, lz in cases:
