@@ -7,32 +7,9 @@
 // the cell, so the RHS is reproduced bit for bit without atomics.
 #pragma once
 
-#include "gas.cuh"
-
-#include <stdint.h>
+#include "generic_types.cuh"
 
 namespace mmf {
-
-struct GenericMesh {
-    int64_t n_cells;
-    int64_t n_ifaces;
-    int64_t stride;           // SoA field stride (>= n_cells)
-    // cell -> ordered interface entries, entry = (interface raw id << 1) | side (0 owner, 1 neigh);
-    // only processed interfaces of solved cells are listed
-    const int64_t *cf_ptr;    // [n_cells + 1]
-    const int32_t *cf_ent;
-    // per interface, raw id indexed
-    const int32_t *f_owner;
-    const int32_t *f_neigh;   // -1 border
-    const int8_t  *f_bc;
-    const double  *f_area;
-    const double  *f_normal;  // SoA [e * n_ifaces + f]
-    // per cell
-    const uint8_t *c_solved;
-    const uint8_t *c_update;  // internal AND solved
-    const double  *c_volume;
-    double dirichlet_info[NF];
-};
 
 // ---- host AoS (raw order, [c*5+k]) <-> device SoA ([k*stride+c]) -------------------------------
 
@@ -133,17 +110,6 @@ __global__ void __launch_bounds__(128) generic_rhs_kernel(GenericMesh m, const d
 // Lets a whole RK3 step (and a batch of steps) be enqueued without any host round trip:
 // dt is chosen on the device from the stage-1 max eigenvalue exactly like src/main.cpp:398-402,
 // and steps enqueued past t_max switch themselves off through `active`.
-struct StepControl {
-    double t, dt, t_max, cfl, min_h, steps, active; // the first seven are (re)set by the host per call
-    double max_eig[3];   // per-stage max face eigenvalue (src/main.cpp:399, :440, :476)
-    double max_eig_chk;  // uniform path: stage-1 face maximum re-derived by the fused kernel
-    // uniform path: max eigenvalue of the state stage 3 wrote, found right behind stage 3 from its
-    // per-tile FP32 estimates (uniform_eig_select_kernel / uniform_eig_tiles_kernel)
-    double eig_next;
-    double est_max;      // largest FP32 eigenvalue estimate over the tiles (all ranks after the all-reduce)
-    double mismatches;   // sticky: steps whose dt eigenvalue differed from stage 1's own face maximum
-};
-constexpr int STEP_CONTROL_HOST_FIELDS = 7;
 
 // ---- RK stage loops (src/main.cpp:409-423, 445-459, 481-495) -----------------------------------
 

@@ -3,7 +3,7 @@
 #pragma once
 
 #include "../../include/mmf_b200.h"
-#include "generic_kernels.cuh"
+#include "generic_types.cuh"
 
 #include <cuda_runtime.h>
 

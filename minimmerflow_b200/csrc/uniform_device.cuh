@@ -1,0 +1,136 @@
+// uniform_device.cuh -- device-side vocabulary of the uniform path: geometry and launch-argument structs,
+// per-cell derived quantities, axis-specialised fluxes, the LLF interface flux.  Templates and inline
+// functions only (no kernels), so that every stage-kernel translation unit can include it.
+// uniform_kernels.cuh describes the layout and the work decomposition.
+#pragma once
+
+#include "generic_types.cuh"
+#include "ptx_helpers.cuh"
+
+namespace mmf {
+
+enum { NUM_MORTON = 0, NUM_LEXI = 1, NUM_AXIS = 2 };
+
+struct UniformGeom {
+    int nx, ny, nz;        // local box (cells)
+    int gx0, gy0, gz0;     // lattice coordinate of the first local cell
+    int gnx, gny, gnz;     // global lattice
+    int px, py, pz;        // padded extents (px = row pitch)
+    long long fs;          // field stride in doubles
+    double h, area, volume;
+    int bc[6];             // physical BC per side (-x,+x,-y,+y,-z,+z); -2 = partition boundary
+    double dirichlet[NF];
+};
+
+// Bounds the stage kernels clamp their LOAD coordinates to.  The virtual state of BC_FREE_FLOW is a
+// copy of the inner cell (src/euler.cpp:298-310), so on such a side the kernels simply read the
+// boundary cell again instead of a ghost cell (ilo = 0 instead of -1, ...): no ghost pass between
+// the stages, bitwise the same fluxes.
+struct LoadClamp {
+    int ilo, ihi, jlo, jhi, klo, khi;
+};
+
+// Multi-GPU, direct peer stores: instead of a wait kernel in front of a stage, the CTAs whose tile
+// touches a partition side wait themselves (one thread per side spins on this rank's arrival
+// counter), and the tiles are visited interior first (tile_order), so that by the time the first
+// boundary tile is scheduled the neighbours' layers have long arrived: the exchange and the rank skew
+// hide behind the interior work of the same kernel.
+struct HaloWait {
+    const unsigned long long *flags; // [6] arrival counters of this rank (nullptr: nothing to wait for)
+    unsigned long long seq;          // value the counters must have reached for the array being read
+    unsigned int mask;               // sides that have a neighbour rank
+    const int *tile_order;           // [tx*ty*tz] tile visited by CTA b (1-D grid); nullptr: 3-D grid
+    int tx, ty, tz;
+};
+
+// Multi-GPU, direct peer stores: ghost cells across an x partition side live in a COMPACT array
+// [field][k+1][j+1] instead of the padded state array.  In the padded array the x ghost column is one
+// 8-byte element per row, so a neighbour could only fill it with 8-byte stores 2 KB apart over NVLink
+// (measured: 50 us per push against 20 us for a y or z layer, and it slowed the stage kernel running
+// next to it).  The stage kernels' halo lanes (i = -1 / i = nx) simply take their column from here.
+struct XGhost {
+    const double *lo, *hi; // ghost columns of the -x / +x side for the array being read; nullptr: padded array
+    long long fs;          // field stride
+    int pitch;             // ny + 2
+};
+
+// Residual input loads go through L2 only: ghost layers are written by the neighbour GPUs while this
+// kernel runs, and a non-coherent L1 line fetched earlier on the same SM could hold the old values
+__device__ __forceinline__ double ldsin(const double *p) { return __ldcg(p); }
+
+__host__ __device__ __forceinline__ long long uoff(const UniformGeom &g, int i, int j, int k)
+{
+    return ((long long) (k + 1) * g.py + (j + 1)) * g.px + (i + 1);
+}
+
+// ---- per-cell derived quantities ---------------------------------------------------------------
+
+struct CellPrim {
+    double rho, u, v, w, p, H, a; // H = eto + p (src/euler.cpp:103,112), a = sqrt(GAMMA*T) (:61)
+};
+
+struct DivConsts {
+    double y_gm1, y_c1, y_vol; // reciprocals of GAMMA-1, 2/(GAMMA-1) and the cell volume
+};
+
+// conservative2primitive (src/utils.cpp:48-63) + the per-side part of evalSplitting/evalFluxes
+// (src/euler.cpp:45-63, 85-103), evaluated once per cell
+__device__ __forceinline__ void derive_cell(const double *c, const DivConsts &dc, CellPrim &q)
+{
+    const double rho = c[FID_RHO];
+    const double y   = rcp_nr(rho);
+    const double rr  = rho * rho;
+    const double yrr = rcp_nr(rr);
+    const double K = div_nr(c[FID_RHO_U] * c[FID_RHO_U] + c[FID_RHO_V] * c[FID_RHO_V] + c[FID_RHO_W] * c[FID_RHO_W], rr, yrr);
+    const double T = div_nr(div_nr(2.0 * c[FID_RHO_E], rho, y) - K, TWO_OVER_GM1, dc.y_c1);
+    q.rho = rho;
+    q.u = div_nr(c[FID_RHO_U], rho, y);
+    q.v = div_nr(c[FID_RHO_V], rho, y);
+    q.w = div_nr(c[FID_RHO_W], rho, y);
+    q.p = rho * T;
+    const double vel2 = q.u * q.u + q.v * q.v + q.w * q.w;
+    const double eto  = div_nr(q.p, GM1, dc.y_gm1) + 0.5 * rho * vel2;
+    q.H = eto + q.p;
+    q.a = sqrt(GAMMA * T);
+}
+
+// evalFluxes with n = +e_AXIS (src/euler.cpp:105-112): u*1 + v*0 + w*0 == u and p*0 == +0 exactly
+template <int AXIS>
+__device__ __forceinline__ void axis_flux(const CellPrim &q, double *F, double &lam)
+{
+    const double un = (AXIS == 0) ? q.u : (AXIS == 1) ? q.v : q.w;
+    const double m  = q.rho * un;
+    F[0] = m;
+    F[1] = (AXIS == 0) ? m * q.u + q.p : m * q.u;
+    F[2] = (AXIS == 1) ? m * q.v + q.p : m * q.v;
+    F[3] = (AXIS == 2) ? m * q.w + q.p : m * q.w;
+    F[4] = un * q.H;
+    lam  = fabs(un) + q.a; // src/euler.cpp:60-66
+}
+
+// LLF splitting (src/euler.cpp:68-72) times the interface area (:239, :245).  Ah = 0.5*area:
+// A*(0.5*x) == (0.5*A)*x bit for bit because scaling by a power of two commutes with rounding.
+__device__ __forceinline__ double llf_area_flux(const double *UL, const double *FL, double lamL,
+                                                const double *UR, const double *FR, double lamR,
+                                                double Ah, double *AF)
+{
+    const double lam = (lamR < lamL) ? lamL : lamR; // std::max(lambdaR, lambdaL)
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+        AF[k] = Ah * ((FR[k] + FL[k]) - lam * (UR[k] - UL[k]));
+    }
+    return lam;
+}
+
+__device__ __forceinline__ double shfl_down_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+
+// ---- the fused stage kernels live in uniform_stage_v3.cuh / uniform_stage_v5.cuh -----------------
+// STAGE 0: RHS only (euler::computeRHS).   Out = RHS array.
+// STAGE 1: W  = U + dt*R(U)/V                         Sin = U,  Out = Wa
+// STAGE 2: W' = 0.75*U + 0.25*(W + dt*R(W)/V)         Sin = Wa, Un = U, Out = Wb
+// STAGE 3: U' = (1./3)*U + (2./3)*(W' + dt*R(W')/V)   Sin = Wb, Un = U, Out = U (in place, pointwise)
+// ORDER: interface numbering convention deciding the per-cell accumulation order (NUM_*).
+constexpr int XW = 30; // cells updated per warp row (32-lane window, 2 overlap)
+
+} // namespace mmf

@@ -2,12 +2,8 @@
 // padded SoA allocation, launch configuration and the per-step kernel sequence.
 #pragma once
 
-#include "mmf_common.cuh"
+#include "uniform_launch.cuh"
 #include "uniform_kernels.cuh"
-#include "uniform_stage_v3.cuh"
-#include "uniform_stage_v5.cuh"
-#include "uniform_stage_v5r.cuh"
-#include "uniform_stage_v6.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -16,58 +12,6 @@
 #include <utility>
 
 namespace mmf {
-
-// which stage-kernel form runs a stage and with how many warps per CTA:
-//   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
-//   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
-//       has been measured on the GPU), '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps),
-//       kept as an independent cross-check
-struct StageShape {
-    char form = 'p';
-    int nw = 16;
-    int lz = 0; // planes per CTA
-};
-
-struct UniformPath {
-    UniformGeom g{};
-    int cell_numbering = NUM_MORTON;  // raw id <-> lattice (ignored when cell_off is set)
-    int iface_numbering = NUM_MORTON; // accumulation order
-    int order_exact = 1;
-    int *cell_off = nullptr;          // optional explicit raw id -> padded offset
-    double *arr[4] = { nullptr, nullptr, nullptr, nullptr }; // U, Wa, Wb, RHS (lazy)
-    int w_cur = 1;                    // which array currently holds field W
-    StageShape shape[4];              // kernel form, CTA size and z chunk per stage (0 = RHS only, 1..3)
-    float *cta_est = nullptr;         // per stage-3 tile: FP32 estimate of the max eigenvalue of what it wrote
-    int *eig_cand = nullptr;          // [0] = number of listed tiles, then their indices
-    int n_tiles3 = 0;
-    bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
-    bool clamp_ff = true;             // no stage runs the v3 form: free-flow ghosts are never read
-    int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
-    double *send_buf[6] = {}, *recv_buf[6] = {};
-    // direct peer stores over NVLink (comm.cuh): the neighbours' state arrays and arrival flags,
-    // mapped through CUDA IPC
-    bool p2p = false;
-    double *peer_arr[6][3] = {};
-    unsigned long long *flags = nullptr;            // [6] arrival counters, written by the neighbours
-    unsigned long long *peer_flags[6] = {};
-    unsigned int *push_count = nullptr;             // blocks of the running push kernel that are done
-    // compact ghost columns for x partition sides (XGhost): one allocation, [side 0/1][array U/Wa/Wb]
-    double *xghost = nullptr;
-    double *peer_xghost[6] = {};
-    long long xg_fs = 0;
-    unsigned long long xchg_seq = 0;
-    unsigned long long arr_seq[3] = { 0, 0, 0 }; // exchange that last refreshed the ghosts of U / Wa / Wb
-    bool halo_inkernel = false;       // boundary CTAs of the stage kernels wait for the neighbours themselves
-    int *tile_order[4] = {};          // per stage shape: interior tiles first, tiles on a partition side last
-    // the push of a stage's output runs on the communication stream, next to the interior tiles of the
-    // following stage; allowed only when every stage has at least one full wave of interior tiles, so
-    // that waiting boundary CTAs can never hold all SMs before the push has been scheduled
-    bool push_async = false;
-    cudaEvent_t ev_stage = nullptr;           // the stage whose output is to be pushed has finished
-    cudaEvent_t ev_push[3] = {};              // the last push that read U / Wa / Wb has finished
-    bool push_pending[3] = { false, false, false };
-    void *ipc_opened[6][5] = {};
-};
 
 inline int uniform_order_exact(const mmf_ctx *ctx) { return ctx->uni ? ctx->uni->order_exact : 0; }
 inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_candidate = false; }
@@ -100,46 +44,6 @@ static int uniform_ensure_rhs(mmf_ctx *ctx)
     return MMF_OK;
 }
 
-// ---- launch helpers -----------------------------------------------------------------------------
-
-// compact x ghost columns are read by the XG = true instantiations, built for the default CTA shapes only
-static bool uniform_use_xghost(const mmf_ctx *ctx)
-{
-    const UniformPath *u = ctx->uni;
-    if (!(ctx->comm && u->p2p && u->halo_inkernel && u->xghost)) return false;
-    if (u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0) return false;
-    for (int st = 0; st < 4; ++st) if (u->shape[st].nw != 12 && u->shape[st].nw != 16) return false;
-    return true;
-}
-
-// free-flow sides: the v5 stage kernels re-read the boundary cell instead of a ghost cell
-static LoadClamp uniform_load_clamp(const UniformPath *u)
-{
-    const UniformGeom &g = u->g;
-    const bool on = u->clamp_ff;
-    LoadClamp lc;
-    lc.ilo = (on && g.bc[0] == BC_FREE_FLOW) ? 0 : -1;
-    lc.ihi = (on && g.bc[1] == BC_FREE_FLOW) ? g.nx - 1 : g.nx;
-    lc.jlo = (on && g.bc[2] == BC_FREE_FLOW) ? 0 : -1;
-    lc.jhi = (on && g.bc[3] == BC_FREE_FLOW) ? g.ny - 1 : g.ny;
-    lc.klo = (on && g.bc[4] == BC_FREE_FLOW) ? 0 : -1;
-    lc.khi = (on && g.bc[5] == BC_FREE_FLOW) ? g.nz - 1 : g.nz;
-    return lc;
-}
-
-// opt-in to more than 48 KB of dynamic shared memory, once per kernel and device
-template <typename K>
-static cudaError_t stage_smem_attribute(K kern, size_t smem)
-{
-    static std::vector<std::pair<const void *, int>> done;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    for (const auto &d : done) if (d.first == (const void *) kern && d.second == dev) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    if (e == cudaSuccess) done.emplace_back((const void *) kern, dev);
-    return e;
-}
-
 // visiting order of the tiles of every stage shape: tiles that touch no partition side first
 static int uniform_build_tile_orders(mmf_ctx *ctx)
 {
@@ -169,109 +73,11 @@ static int uniform_build_tile_orders(mmf_ctx *ctx)
     return MMF_OK;
 }
 
-template <typename K>
-static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const UniformGeom &g = u->g;
-    const int nw = 12, lz = u->shape[stage].lz;
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
-    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
-    {
-        ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz);
-    }
-    MMF_LAUNCH_CHECK(ctx);
-    return MMF_OK;
-}
-
-template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
-                          double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const UniformGeom &g = u->g;
-    const int lz = u->shape[stage].lz;
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
-    for (int q = 0; q < 3; ++q) {
-        if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
-            MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
-            u->push_pending[q] = false;
-        }
-    }
-    HaloWait hw{};
-    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
-    if (ctx->comm && u->p2p && u->halo_inkernel) {
-        int a = -1;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
-        for (int s = 0; s < 6; ++s) hw.mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
-        if (a >= 0 && hw.mask) {
-            hw.flags = u->flags;
-            hw.seq = u->arr_seq[a];
-            hw.tile_order = u->tile_order[stage];
-            if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
-        }
-    }
-    XGhost xg{};
-    if (hw.flags && uniform_use_xghost(ctx)) { // x ghosts of partition sides come from the compact columns
-        int a = 0;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
-        xg.fs = u->xg_fs;
-        xg.pitch = g.ny + 2;
-        if (u->nbr_rank[0] >= 0) xg.lo = u->xghost + (size_t) (0 * 3 + a) * NF * u->xg_fs;
-        if (u->nbr_rank[1] >= 0) xg.hi = u->xghost + (size_t) (1 * 3 + a) * NF * u->xg_fs;
-    }
-    {
-        ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u), hw, xg);
-    }
-    MMF_LAUNCH_CHECK(ctx);
-    return MMF_OK;
-}
-
-template <int STAGE, int ORDER>
-static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const StageShape sh = u->shape[STAGE];
-    if (sh.form == '3') return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
-    const bool xgk = uniform_use_xghost(ctx);
-    // v5 forms: record (11) + flux (5) doubles per lane and row, two mbarriers per row; v6: twice that
-#define MMF_SMEM_V5(NWV) ((size_t) (NWV) * 16 * 32 * sizeof(double) + 2 * (NWV) * sizeof(unsigned long long))
-#define MMF_LAUNCH6(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v6<STAGE, ORDER, NWV, XGV>, STAGE, NWV, stage_v6_smem_bytes(NWV), Sin, Un, Out, d_max)
-#define MMF_LAUNCH(KERN, NWV, XGV) return launch_stage_k(ctx, KERN<STAGE, ORDER, NWV, XGV>, STAGE, NWV, MMF_SMEM_V5(NWV), Sin, Un, Out, d_max)
-    if (sh.form == 'd') {
-        if (sh.nw == 16) { if (xgk) MMF_LAUNCH6(16, true); MMF_LAUNCH6(16, false); }
-        if (sh.nw == 8) MMF_LAUNCH6(8, false);
-        if (xgk) MMF_LAUNCH6(12, true);
-        MMF_LAUNCH6(12, false);
-    }
-    if (sh.form == 'r') {
-        if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5r, 16, false); }
-        if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5r, 8, false);
-        if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5r, 12, true);
-        MMF_LAUNCH(uniform_stage_kernel_v5r, 12, false);
-    }
-    if (sh.nw == 16) { if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 16, true); MMF_LAUNCH(uniform_stage_kernel_v5, 16, false); }
-    if (sh.nw == 8) MMF_LAUNCH(uniform_stage_kernel_v5, 8, false);
-    if (xgk) MMF_LAUNCH(uniform_stage_kernel_v5, 12, true);
-    MMF_LAUNCH(uniform_stage_kernel_v5, 12, false);
-#undef MMF_LAUNCH
-#undef MMF_LAUNCH6
-#undef MMF_SMEM_V5
-}
-
 template <int STAGE>
 static int launch_stage(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
 {
-    switch (ctx->uni->iface_numbering) {
-    case NUM_MORTON: return launch_stage_o<STAGE, NUM_MORTON>(ctx, Sin, Un, Out, d_max);
-    case NUM_LEXI:   return launch_stage_o<STAGE, NUM_LEXI>(ctx, Sin, Un, Out, d_max);
-    default:         return launch_stage_o<STAGE, NUM_AXIS>(ctx, Sin, Un, Out, d_max);
-    }
+    const UniformPath *u = ctx->uni;
+    return stage_launcher(u->shape[STAGE].form, STAGE)(ctx, u->iface_numbering, Sin, Un, Out, d_max);
 }
 
 int comm_uniform_exchange_enqueue(mmf_ctx *ctx, double *S, bool defer_wait); // comm.cuh

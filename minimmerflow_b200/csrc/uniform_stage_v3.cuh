@@ -15,7 +15,7 @@
 // every kernel version).
 #pragma once
 
-#include "uniform_kernels.cuh"
+#include "uniform_device.cuh"
 
 namespace mmf {
 

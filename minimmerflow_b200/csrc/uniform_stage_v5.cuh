@@ -26,7 +26,7 @@
 // results stay bit-identical to the CPU restatement of the reference (tests/test_uniform_gpu.py).
 #pragma once
 
-#include "uniform_stage_v3.cuh"
+#include "uniform_device.cuh"
 
 namespace mmf {
 
