@@ -31,6 +31,10 @@
 
 #include <type_traits>
 
+#ifndef MMF_V6_LATE_UN
+#define MMF_V6_LATE_UN 1
+#endif
+
 namespace mmf {
 
 // dynamic shared memory of the v6 kernels: records (11) + fluxes (5) doubles per lane, row and slot,
@@ -185,7 +189,12 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
         const double *f_up = sm_f + (row + 1) * NF * 32 + lane;
 
         const double *sp  = scol + (long long) (max(z0 - 1, lc.klo) + 1) * splane; // plane z0-1 (clamped)
-        const double *unp = Un + col + (long long) (z0 + 1) * plane; // plane z0
+        // U^n of a plane is needed when the plane is finished, one iteration after its residual input.
+        // LATE_UN loads it at the top of THAT iteration (consumed a third of an iteration later: enough to
+        // cover the DRAM latency) instead of carrying it across the loop edge: 10 registers less at the
+        // pressure peak, which is what the 16-warp (128-register) builds of stages 2 and 3 lack.
+        constexpr bool LATE_UN = MMF_V6_LATE_UN;
+        const double *unp = Un + col + (long long) (z0 + (LATE_UN ? 0 : 1)) * plane; // plane z0 (LATE_UN: z0-1)
         double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
 
         double pU[NF], pFz[NF], plz, pS[NF], pUn[NF], nxt[NF];
@@ -217,9 +226,13 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
 #pragma unroll
             for (int k = 0; k < NF; ++k) nxt[k] = ldsin(sp + k * sfs);
             double cUn[NF];
-            if (STAGE >= 2 && upd) {
+            if (STAGE >= 2 && upd && !LATE_UN) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) cUn[k] = unp[k * fs];
+            }
+            if (STAGE >= 2 && upd && LATE_UN && it > 0) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pUn[k] = unp[k * fs];
             }
             unp += plane;
 
@@ -343,7 +356,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pU[k] = cU[k]; pFz[k] = cFz[k]; }
             plz = clz;
-            if (STAGE >= 2) {
+            if (STAGE >= 2 && !LATE_UN) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pUn[k] = cUn[k];
             }
@@ -362,6 +375,10 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
 
         // ---- epilogue: plane z1 only closes the last z interface; plane z1-1 still lacks -y_hi ------
         {
+            if (STAGE >= 2 && upd && LATE_UN) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pUn[k] = unp[k * fs];
+            }
             CellPrim q;
             derive_cell(nxt, dc, q);
             double cFz[NF], clz, AFz[NF];
