@@ -1,5 +1,5 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<p|r|d|t> -DMMF_TU_FORM_ID=<0..3> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<p|r|d|t|h> -DMMF_TU_FORM_ID=<0..4> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 #include "uniform_launch.cuh"
 
@@ -13,12 +13,12 @@
 #include "uniform_stage_v5.cuh"
 #elif MMF_TU_FORM_ID == 1
 #include "uniform_stage_v5r.cuh"
-#elif MMF_TU_FORM_ID == 2
+#elif MMF_TU_FORM_ID == 2 || MMF_TU_FORM_ID == 4
 #include "uniform_stage_v6.cuh"
 #elif MMF_TU_FORM_ID == 3
 #include "uniform_stage_v3.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d) or 3 (t)"
+#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t) or 4 (h)"
 #endif
 
 namespace mmf {
@@ -34,8 +34,9 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 #else
     const bool xgk = uniform_use_xghost(ctx);
     // v5 forms: record (11) + flux (5) doubles per lane and row, two mbarriers per row; v6: twice that
-#if MMF_TU_FORM_ID == 2
-#define MMF_LAUNCH(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v6<STAGE, ORDER, NWV, XGV>, STAGE, NWV, stage_v6_smem_bytes(NWV), Sin, Un, Out, d_max)
+#if MMF_TU_FORM_ID == 2 || MMF_TU_FORM_ID == 4
+#define MMF_MH (MMF_TU_FORM_ID == 4)
+#define MMF_LAUNCH(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v6<STAGE, ORDER, NWV, XGV, MMF_MH>, STAGE, NWV, stage_v6_smem_bytes(NWV, MMF_MH), Sin, Un, Out, d_max)
 #else
 #if MMF_TU_FORM_ID == 1
 #define MMF_KERN uniform_stage_kernel_v5r

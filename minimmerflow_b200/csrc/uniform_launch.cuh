@@ -16,12 +16,15 @@ namespace mmf {
 // which stage-kernel form runs a stage and with how many warps per CTA:
 //   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
 //   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
-//       has been measured on the GPU), '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps),
+//       has been measured on the GPU), 'h' the same with ONE warp serving both halo rows (a CTA updates
+//       nw-1 rows instead of nw-2; opt-in likewise), '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps),
 //       kept as an independent cross-check
 struct StageShape {
     char form = 'p';
     int nw = 16;
     int lz = 0; // planes per CTA
+    // y rows a CTA updates: all warps but the two halo rows; form 'h' serves both halo rows with one warp
+    int rows() const { return form == 'h' ? nw - 1 : nw - 2; }
 };
 
 struct UniformPath {
@@ -128,8 +131,8 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, 
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    const int lz = u->shape[stage].lz;
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
+    const int lz = u->shape[stage].lz, rows = u->shape[stage].rows();
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
     MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     for (int q = 0; q < 3; ++q) {
         if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
@@ -182,19 +185,21 @@ typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const d
 MMF_DECLARE_STAGE_TUS(p)  // uniform_stage_v5.cuh
 MMF_DECLARE_STAGE_TUS(r)  // uniform_stage_v5r.cuh
 MMF_DECLARE_STAGE_TUS(d)  // uniform_stage_v6.cuh
+MMF_DECLARE_STAGE_TUS(h)  // uniform_stage_v6.cuh, one warp for both halo rows
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_v3.cuh (form '3')
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('p', 'r', 'd', '3') for a stage
+// the launcher of a kernel form ('p', 'r', 'd', 'h', '3') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[4][4] = {
+    static const StageLauncher tab[5][4] = {
         { launch_stage_p_0, launch_stage_p_1, launch_stage_p_2, launch_stage_p_3 },
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
         { launch_stage_d_0, launch_stage_d_1, launch_stage_d_2, launch_stage_d_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
+        { launch_stage_h_0, launch_stage_h_1, launch_stage_h_2, launch_stage_h_3 },
     };
-    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : 0;
+    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : 0;
     return tab[f][stage];
 }
 

@@ -52,7 +52,7 @@ static int uniform_build_tile_orders(mmf_ctx *ctx)
     u->push_async = u->halo_inkernel && !(getenv("MMF_PUSH_SYNC") && atoi(getenv("MMF_PUSH_SYNC")));
     for (int st = 0; st < 4; ++st) {
         const StageShape &sh = u->shape[st];
-        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + sh.nw - 3) / (sh.nw - 2), tz = (g.nz + sh.lz - 1) / sh.lz;
+        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + sh.rows() - 1) / sh.rows(), tz = (g.nz + sh.lz - 1) / sh.lz;
         std::vector<int> inner, outer;
         for (int t = 0; t < tx * ty * tz; ++t) {
             const int bx = t % tx, by = (t / tx) % ty, bz = t / (tx * ty);
@@ -123,7 +123,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (164-166
     // registers, no spills) the fastest for stages 2 and 3, which also stream U^n.
     // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "d12" = the decoupled form
-    // everywhere, "312" = v3 everywhere.
+    // everywhere, "h12" = decoupled with a merged halo warp, "312" = v3 everywhere.
     const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
     for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
@@ -135,7 +135,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != 'h' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
@@ -151,7 +151,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     for (int st = 0; st < 4; ++st) {
         StageShape &sh = u->shape[st];
         if (env_lz && atoi(env_lz) > 0) { sh.lz = atoi(env_lz); continue; }
-        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.nw - 3) / (sh.nw - 2));
+        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.rows() - 1) / sh.rows());
         const double sms = (double) ctx->prop.multiProcessorCount;
         double best = -1.;
         for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 16); ++chunks) {
@@ -165,7 +165,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     }
     {
         const StageShape &s3 = u->shape[3];
-        u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.nw - 3) / (s3.nw - 2)) * ((g.nz + s3.lz - 1) / s3.lz);
+        u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.rows() - 1) / s3.rows()) * ((g.nz + s3.lz - 1) / s3.lz);
         if ((rc = dev_alloc(ctx, &u->cta_est, (size_t) u->n_tiles3))) return rc;
         if ((rc = dev_alloc(ctx, &u->eig_cand, (size_t) u->n_tiles3 + 1))) return rc;
     }
@@ -477,13 +477,13 @@ static int uniform_step(mmf_ctx *ctx)
     if (s3.form != '3') {
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
-        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.nw - 3) / (s3.nw - 2);
+        const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.rows() - 1) / s3.rows();
         uniform_eig_estmax_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max);
         MMF_LAUNCH_CHECK(ctx);
         if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->est_max, 1))) return rc;
         uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max, u->eig_cand);
         MMF_LAUNCH_CHECK(ctx);
-        uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 320, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.nw - 2,
+        uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 320, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.rows(),
                                                                                              s3.lz, &c->eig_next);
         MMF_LAUNCH_CHECK(ctx);
         u->eig_candidate = true;

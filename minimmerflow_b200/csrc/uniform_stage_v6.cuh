@@ -39,10 +39,15 @@ namespace mmf {
 
 // dynamic shared memory of the v6 kernels: records (11) + fluxes (5) doubles per lane, row and slot,
 // four mbarriers per row
-__host__ __device__ constexpr size_t stage_v6_smem_bytes(int nw)
+// (merged halo: one more virtual row, see MH below)
+__host__ __device__ constexpr size_t stage_v6_smem_bytes(int nw, bool merged_halo = false)
 {
-    return (size_t) 2 * nw * 16 * 32 * sizeof(double) + (size_t) 4 * nw * sizeof(unsigned long long);
+    return (size_t) 2 * (nw + (merged_halo ? 1 : 0)) * 16 * 32 * sizeof(double) +
+           (size_t) 4 * (nw + (merged_halo ? 1 : 0)) * sizeof(unsigned long long);
 }
+
+// cells a CTA of nw warps updates along y
+__host__ __device__ constexpr int stage_v6_rows(int nw, bool merged_halo) { return merged_halo ? nw - 1 : nw - 2; }
 
 // The plane loop, two planes per trip with the slot (= plane parity) a compile-time constant in each
 // copy of the body, so that slot offsets fold into the shared-memory addresses.
@@ -51,7 +56,13 @@ __host__ __device__ constexpr size_t stage_v6_smem_bytes(int nw)
         _Pragma("unroll") for (int SLOT = 0; SLOT < 2; ++SLOT)                                              \
             if (IT0 + SLOT < z1 - z0)
 
-template <int STAGE, int ORDER, int NW, bool XG>
+// MH ("merged halo", kernel form 'h'): ONE warp serves both halo rows of the tile -- it publishes the record of
+// the row below the tile and turns the record of the tile's top row into that row's -y_hi flux -- so a CTA
+// of NW warps updates NW-1 rows instead of NW-2 (11 of 12 warps do full work instead of 10; with three
+// warps per scheduler the two schedulers that hosted a halo row were under-used anyway).  The halo warp
+// handles its top part one plane late (plane it-1 in iteration it): the flux is only consumed one plane
+// later by the decoupled scheme, and the halo warp then practically never waits.
+template <int STAGE, int ORDER, int NW, bool XG, bool MH = false>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
@@ -59,18 +70,20 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
 {
     extern __shared__ double smem[];
     // sm_d[slot][row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[slot][row][k][lane] = area * flux of (j-1 | j)
-    constexpr int DS = NW * 11 * 32, FS = NW * NF * 32; // doubles per slot
+    constexpr int NR = MH ? NW + 1 : NW;                 // rows of the exchange buffers (MH: virtual row NW on top)
+    constexpr int RT = stage_v6_rows(NW, MH);            // rows updated per tile
+    constexpr int DS = NR * 11 * 32, FS = NR * NF * 32;  // doubles per slot
     double *sm_d = smem;
     double *sm_f = smem + 2 * DS;
     unsigned long long *barD = reinterpret_cast<unsigned long long *>(sm_f + 2 * FS); // [slot][row]: record published
-    unsigned long long *barF = barD + 2 * NW;                                          // [slot][row]: low y flux published
+    unsigned long long *barF = barD + 2 * NR;                                          // [slot][row]: low y flux published
 
     if (STAGE >= 1 && ctl->active == 0.0) return;
 
     const int lane = threadIdx.x & 31;
     const int row  = threadIdx.x >> 5;
     const TileId tid = stage_tile(hw);
-    if (threadIdx.x < 2 * NW) {
+    if (threadIdx.x < 2 * NR) {
         mbar_init(&barD[threadIdx.x], 1);
         mbar_init(&barF[threadIdx.x], 1);
     }
@@ -78,7 +91,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
     __syncthreads();
 
     const int i  = tid.bx * XW - 1 + lane;
-    const int j  = tid.by * (NW - 2) - 1 + row;
+    const int j  = tid.by * RT - 1 + row;
     const int z0 = tid.bz * lz;
     const int z1 = min(z0 + lz, g.nz);
     const int ic = min(max(i, lc.ilo), lc.ihi); // load coordinates (free-flow sides re-read the boundary cell)
@@ -105,7 +118,80 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
     double lmax = 0.0;
     float emax = 0.f;
 
-    if (row == 0) {
+    if (MH && row == 0) {
+        // ================= merged halo warp ==========================================================
+        // bottom: row j = tile_j0 - 1, publishes (U, Fy, lam_y) for row 1;  top: virtual row NW (j = tile_j0 - 1
+        // + NW), turns the record of row NW-1 into the flux of the face between them, one plane late.
+        const int jt  = j + NW;
+        const int jtc = min(max(jt, lc.jlo), lc.jhi);
+        const bool yf_ok = in_x && lane >= 1 && lane <= XW && jt >= 0 && jt <= g.ny;
+        const double *scol_t = Sin + (long long) (jtc + 1) * g.px + (ic + 1);
+        if (XG) {
+            if (xg.lo && i < 0)     scol_t = xg.lo + (jtc + 1);
+            if (xg.hi && i >= g.nx) scol_t = xg.hi + (jtc + 1);
+        }
+        const double *sp_b = scol + (long long) (z0 + 1) * splane;   // plane z0
+        const double *sp_t = scol_t + (long long) (z0 + 1) * splane;
+        const int n = z1 - z0;
+        double lmy = 0.0;
+        double nb[NF], nt[NF];     // prefetched plane `it` of the bottom / top row
+        double tU[NF], tFy[NF], tly = 0.0; // top row, plane it-1
+#pragma unroll
+        for (int k = 0; k < NF; ++k) { nb[k] = ldsin(sp_b + k * sfs); nt[k] = ldsin(sp_t + k * sfs); tU[k] = 0.0; tFy[k] = 0.0; }
+#pragma unroll 1
+        for (int it = 0; it <= n; ++it) {
+            const int slot = it & 1;
+            double bU[NF], cT[NF], bFy[NF], bly = 0.0, cFy[NF], cly = 0.0;
+            if (it < n) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { bU[k] = nb[k]; cT[k] = nt[k]; }
+                sp_b += splane;
+                sp_t += splane;
+                if (it + 1 < n) {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) { nb[k] = ldsin(sp_b + k * sfs); nt[k] = ldsin(sp_t + k * sfs); }
+                }
+                CellPrim qb, qt; // two independent chains
+                derive_cell(bU, dc, qb);
+                derive_cell(cT, dc, qt);
+                axis_flux<1>(qb, bFy, bly);
+                axis_flux<1>(qt, cFy, cly);
+                // bottom record `it`.  The slot still holds record it-2: row 1 has read it once its flux it-2 is
+                // out, and it cannot complete that barrier again before it has seen record `it`.
+                if (it >= 2) mbar_wait(&barF[slot * NR + 1], (unsigned) (((it - 2) >> 1) & 1));
+                double *d = sm_d + slot * DS + lane;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { d[k * 32] = bU[k]; d[(NF + k) * 32] = bFy[k]; }
+                d[10 * 32] = bly;
+                mbar_arrive_elect(&barD[slot * NR + 0], lane);
+            }
+            if (it >= 1) {
+                // top flux of plane it-1.  Row NW-1 publishes record it+1 on this barrier only at the top of
+                // its iteration it+1, after its iteration `it` has taken the flux written here.
+                const int ps = (it - 1) & 1;
+                mbar_wait(&barD[ps * NR + NW - 1], (unsigned) (((it - 1) >> 1) & 1));
+                const double *d_dn = sm_d + ps * DS + (NW - 1) * 11 * 32 + lane;
+                double lU[NF], lF[NF], AFy[NF];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
+                const double ll  = d_dn[10 * 32];
+                const double lam = llf_area_flux(lU, lF, ll, tU, tFy, tly, Ah, AFy);
+                lmy = (lam < lmy) ? lmy : lam;
+                // the slot held flux it-3: row NW-1 took it during its plane it-2, before it published the
+                // record it-1 this warp has just waited for
+                double *f = sm_f + ps * FS + NW * NF * 32 + lane;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
+                mbar_arrive_elect(&barF[ps * NR + NW], lane);
+            }
+            if (it < n) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { tU[k] = cT[k]; tFy[k] = cFy[k]; }
+                tly = cly;
+            }
+        }
+        lmax = yf_ok ? lmy : 0.0;
+    } else if (!MH && row == 0) {
         // ================= low halo row: publishes (U, Fy, lam_y) of row j for row 1 =================
         const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
         double nxt[NF];
@@ -128,13 +214,13 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             axis_flux<1>(q, cFy, cly);
             // the slot still holds record it-2: row 1 has read it once its flux it-2 is out.  Row 1 cannot
             // complete this barrier again before it has seen record `it`, which follows this wait.
-            if (it >= 2) mbar_wait(&barF[slot * NW + 1], (unsigned) (((it - 2) >> 1) & 1));
+            if (it >= 2) mbar_wait(&barF[slot * NR + 1], (unsigned) (((it - 2) >> 1) & 1));
 #pragma unroll
             for (int k = 0; k < NF; ++k) { d[k * 32] = cU[k]; d[(NF + k) * 32] = cFy[k]; }
             d[10 * 32] = cly;
-            mbar_arrive_elect(&barD[slot * NW + 0], lane);
+            mbar_arrive_elect(&barD[slot * NR + 0], lane);
         }
-    } else if (row == NW - 1) {
+    } else if (!MH && row == NW - 1) {
         // ================= high halo row: computes the y face (j-1 | j) for row NW-2 ================
         const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;
         const double *sp = scol + (long long) (z0 + 1) * splane; // plane z0
@@ -159,7 +245,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
             // row NW-2 publishes record it+2 on this barrier only after it has taken flux `it`, below
-            mbar_wait(&barD[slot * NW + NW - 2], (unsigned) ((it >> 1) & 1));
+            mbar_wait(&barD[slot * NR + NW - 2], (unsigned) ((it >> 1) & 1));
             double lU[NF], lF[NF], AFy[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
@@ -169,7 +255,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             // the slot held flux it-2: row NW-2 took it during its plane it-1, before it published record `it`
 #pragma unroll
             for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
-            mbar_arrive_elect(&barF[slot * NW + NW - 1], lane);
+            mbar_arrive_elect(&barF[slot * NR + NW - 1], lane);
         }
         lmax = yf_ok ? lmy : 0.0;
     } else {
@@ -249,7 +335,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
                 for (int k = 0; k < NF; ++k) { d[k * 32] = cU[k]; d[(NF + k) * 32] = cFy[k]; }
                 d[10 * 32] = cly;
             }
-            mbar_arrive_elect(&barD[slot * NW + row], lane);
+            mbar_arrive_elect(&barD[slot * NR + row], lane);
 
             // ---- z interface (kz-1 | kz) ---------------------------------------------------------------
             double cFz[NF], clz, AFz[NF];
@@ -262,7 +348,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             // row+1 completes this barrier again (flux it+1) only after it has seen record it+1 of this
             // row, which is published in the next iteration, after this wait.
             if (ORDER != NUM_AXIS && it > 0 && g.gz0 + kz - 1 != 0) {
-                mbar_wait(&barF[(slot ^ 1) * NW + row + 1], (unsigned) (((it - 1) >> 1) & 1));
+                mbar_wait(&barF[(slot ^ 1) * NR + row + 1], (unsigned) (((it - 1) >> 1) & 1));
                 const double *f = f_up + (slot ^ 1) * FS;
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];
@@ -285,7 +371,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             // ---- y interface (j-1 | j): row-1's record through shared memory --------------------------
             // row-1 publishes record it+2 on this barrier only after it has taken this row's flux `it`
             double AFy[NF];
-            mbar_wait(&barD[slot * NW + row - 1], par);
+            mbar_wait(&barD[slot * NR + row - 1], par);
             {
                 const double *d = d_dn + slot * DS;
                 double lU[NF], lF[NF];
@@ -299,7 +385,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
                 double *f = f_own + slot * FS;
 #pragma unroll
                 for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
-                mbar_arrive_elect(&barF[slot * NW + row], lane);
+                mbar_arrive_elect(&barF[slot * NR + row], lane);
             }
 
             // ---- ordered accumulation (src/euler.cpp:153, 237-247) ------------------------------------
@@ -344,7 +430,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             }
             // -y_hi follows one plane later, except where a +z_lo term has to come behind it
             if (ORDER == NUM_AXIS || key_z < 0) {
-                mbar_wait(&barF[slot * NW + row + 1], par);
+                mbar_wait(&barF[slot * NR + row + 1], par);
                 const double *f = f_up + slot * FS;
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];
@@ -387,7 +473,7 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             lmz = (lam < lmz) ? lmz : lam;
             const int it = z1 - z0; // the iteration that would follow
             if (ORDER != NUM_AXIS && g.gz0 + z1 - 1 != 0) {
-                mbar_wait(&barF[((it - 1) & 1) * NW + row + 1], (unsigned) (((it - 1) >> 1) & 1));
+                mbar_wait(&barF[((it - 1) & 1) * NR + row + 1], (unsigned) (((it - 1) >> 1) & 1));
                 const double *f = f_up + ((it - 1) & 1) * FS;
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pS[k] -= f[k * 32];

@@ -189,7 +189,8 @@ std::function<void()> bind_kernel(int form, const Args &a)
     case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
 #ifdef MMF_EMU_HAVE_V6
-    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
 #endif
     default: return nullptr;
     }
@@ -258,7 +259,8 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     a.max_eig = max_eig;
     a.lz = lz;
     a.cta_est = cta_est;
-    const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + (nw - 2) - 1) / (nw - 2), gz = (g.nz + lz - 1) / lz;
+    const int rows = (form == 'h') ? nw - 1 : nw - 2; // rows a tile updates
+    const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + rows - 1) / rows, gz = (g.nz + lz - 1) / lz;
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;
     a.xg = XGhost{};

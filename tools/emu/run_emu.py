@@ -125,15 +125,17 @@ class Box:
                     arr[:, og] = out
 
     def smem_doubles(self, form, nw):
-        if form == "d":
-            return nw * 2 * 16 * 32 + 4 * nw  # double-buffered records and fluxes, two mbarriers per slot and row
+        if form in ("d", "h"):
+            nr = nw + (1 if form == "h" else 0)   # merged halo: one more (virtual) row
+            return nr * 2 * 16 * 32 + 4 * nr      # double-buffered records and fluxes, two mbarriers per slot and row
         return nw * 16 * 32 + 2 * nw
 
     def stage(self, form, stage, nw, lz, Sin, Un, Out, dt, chaos=0, seed=1):
         m = self.m
         me = np.zeros(1)
         nx, ny, nz = (int(v) for v in self.dims)
-        ntiles = ((nx + 29) // 30) * ((ny + nw - 3) // (nw - 2)) * ((nz + lz - 1) // lz)
+        rows = nw - 1 if form == "h" else nw - 2
+        ntiles = ((nx + 29) // 30) * ((ny + rows - 1) // rows) * ((nz + lz - 1) // lz)
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
         dirichlet = np.zeros(5)
@@ -200,7 +202,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="p,r,d")
+    ap.add_argument("--forms", default="p,r,d,h")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -210,8 +212,8 @@ def main():
     lib = load()
     oracle = oracle_lib.load()
     forms = [f for f in args.forms.split(",") if f]
-    if "d" in forms and not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        forms.remove("d")
+    if not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
+        forms = [f for f in forms if f not in ("d", "h")]
     cases = []
     m = oracle.problem_mesh("vortex_xy", 3, 16)
     cases.append(("vortex 16^3 morton", m, 0, 6))
