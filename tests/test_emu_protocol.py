@@ -65,3 +65,31 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
         out[form] = box.gather(R)
     assert np.array_equal(out["r"], out["d"]) and np.array_equal(out["r"], out["h"])
     assert np.abs(out["d"] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("form", ["r", "d", "h"])
+def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
+    """Multi-GPU layout of an x partition side (XGhost): the halo lanes i = -1 / i = nx take their column
+    from compact arrays [field][k+1][j+1] instead of the padded array.  Here the columns hold the
+    reflecting-wall virtual states, and the padded array's own x ghost columns are poisoned with NaNs."""
+    import ctypes as C
+    D = C.POINTER(C.c_double)
+    m = lexicographic_box_mesh(33, 12, 5, 0.5, 1)
+    m["problem"] = "radsod"
+    nc = m["volume"].shape[0]
+    rng = np.random.default_rng(3)
+    rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-0.4, 0.4, (nc, 3)); p = rng.uniform(0.6, 1.4, nc)
+    U0 = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+    ref, ref_eig = oracle.compute_rhs(m, U0)
+    box = run_emu.Box(emu, oracle, dict(m), 1)
+    U, R = box.new_array(), box.new_array()
+    box.scatter(U, U0)
+    box.fill_ghosts(U)
+    lo, hi, fs, pitch = box.compact_x_ghosts(U)
+    emu.emu_set_xghost(lo.ctypes.data_as(D), hi.ctypes.data_as(D), fs, pitch)
+    try:
+        eig, _ = box.stage(form, 0, 12, 3, U, U, R, 0.0, 100, 9)
+    finally:
+        emu.emu_set_xghost(None, None, 0, 0)
+    assert eig == ref_eig
+    assert np.array_equal(box.gather(R), ref)

@@ -182,9 +182,25 @@ struct Args {
     XGhost xg;
 };
 
+// compact x ghost columns (XG = true instantiations): the 12-warp shapes only, to bound the build time
+template <int STAGE, int ORDER>
+std::function<void()> bind_kernel_xg(int form, const Args &a)
+{
+    switch (form) {
+    case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+#ifdef MMF_EMU_HAVE_V6
+    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+#endif
+    default: return nullptr;
+    }
+}
+
 template <int STAGE, int ORDER, int NW>
 std::function<void()> bind_kernel(int form, const Args &a)
 {
+    if (a.xg.lo || a.xg.hi) return (NW == 12) ? bind_kernel_xg<STAGE, ORDER>(form, a) : nullptr;
     switch (form) {
     case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
@@ -220,7 +236,15 @@ std::function<void()> bind_order(int order, int form, int nw, const Args &a)
 
 } // namespace
 
+static mmf::XGhost g_xghost{};
+
 extern "C" {
+
+// compact x ghost columns [field][k+1][j+1] for the NEXT emu_stage calls (nullptr, nullptr: padded array)
+void emu_set_xghost(const double *lo, const double *hi, long long fs, int pitch)
+{
+    g_xghost.lo = lo; g_xghost.hi = hi; g_xghost.fs = fs; g_xghost.pitch = pitch;
+}
 
 // padded extents of a box, as uniform_alloc (uniform_path.cuh) lays them out
 void emu_padded(const int dims[3], int pad[3], long long *fs)
@@ -263,7 +287,7 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + rows - 1) / rows, gz = (g.nz + lz - 1) / lz;
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;
-    a.xg = XGhost{};
+    a.xg = g_xghost;
     if ((size_t) smem_doubles * sizeof(double) > sizeof(mmf::smem)) return -2;
 
     std::function<void()> body;

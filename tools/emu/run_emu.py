@@ -51,6 +51,7 @@ def load():
     lib.emu_stage.argtypes = [C.c_int] * 5 + [_I, _I, _I, _I, C.c_double, C.c_double, C.c_double, _D, _I,
                                               _D, _D, _D, C.c_double, _D, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_uint]
     lib.emu_set_spin_limit.argtypes = [C.c_longlong]
+    lib.emu_set_xghost.argtypes = [_D, _D, C.c_longlong, C.c_int]
     return lib
 
 
@@ -123,6 +124,24 @@ class Box:
                     self.oracle.lib.orc_eval_interface_bc_values(prob, bc, point.ctypes.data_as(_D), n.ctypes.data_as(_D),
                                                                  cons.ctypes.data_as(_D), out.ctypes.data_as(_D))
                     arr[:, og] = out
+
+    def compact_x_ghosts(self, arr):
+        """The XGhost layout of the multi-GPU path: the x ghost columns of `arr` as compact arrays
+        [field][k+1][j+1]; the padded array's own x ghost columns are then poisoned, so a kernel that still
+        read them would produce NaNs."""
+        nx, ny, nz = (int(v) for v in self.dims)
+        px, py, pz = (int(v) for v in self.pad)
+        pitch = ny + 2
+        fs = (pitch * (nz + 2) + 15) // 16 * 16
+        lo = np.empty((5, fs)); hi = np.empty((5, fs))
+        lo[:] = np.array([1.0, 0.0, 0.0, 0.0, 2.5])[:, None]
+        hi[:] = lo
+        vol = arr[:, :px * py * pz].reshape(5, pz, py, px)
+        lo[:, :pitch * (nz + 2)] = vol[:, :, :, 0].reshape(5, -1)
+        hi[:, :pitch * (nz + 2)] = vol[:, :, :, nx + 1].reshape(5, -1)
+        vol[:, :, :, 0] = np.nan
+        vol[:, :, :, nx + 1] = np.nan
+        return lo, hi, fs, pitch
 
     def smem_doubles(self, form, nw):
         if form in ("d", "h"):

@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call for the stage-kernel forms that were developed on the CPU emulator (tools/emu) and have
+# never run on a GPU: parity first, then the sweep that decides whether they become the default.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_first_call.sh'
+# Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+export MMF_TEST_EXPERIMENTAL=1
+# 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp), bounded
+timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps" > gpurun_out/experimental_parity.log 2>&1
+echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
+tail -5 gpurun_out/experimental_parity.log
+# 2. sweep at the benchmark size: per-stage kernel times, bitwise equality with the default mix
+timeout 600 python tools/stage_sweep.py --size 256 --steps 6 > gpurun_out/stage_sweep_256.jsonl 2> gpurun_out/stage_sweep_256.err
+cat gpurun_out/stage_sweep_256.jsonl
+# 3. z-chunk sensitivity of the two most promising mixes
+for lz in 26 32 43 52 64; do
+  timeout 300 python tools/stage_sweep.py --size 256 --steps 6 --variants "p16:p16:h12:h12@$lz,p16:p16:d12:d12@$lz,p16:p16:r12:r12@$lz" >> gpurun_out/stage_sweep_lz.jsonl 2>> gpurun_out/stage_sweep_256.err
+done
+cat gpurun_out/stage_sweep_lz.jsonl
