@@ -18,3 +18,4 @@ for lz in 26 32 43 52 64; do
   timeout 300 python tools/stage_sweep.py --size 256 --steps 6 --variants "p16:p16:h12:h12@$lz,p16:p16:d12:d12@$lz,p16:p16:r12:r12@$lz" >> gpurun_out/stage_sweep_lz.jsonl 2>> gpurun_out/stage_sweep_256.err
 done
 cat gpurun_out/stage_sweep_lz.jsonl
+timeout 600 python tools/generic_bench.py --size 128 --steps 6 > gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err; cat gpurun_out/generic_bench_128.jsonl
