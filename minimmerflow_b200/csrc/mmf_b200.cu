@@ -142,9 +142,10 @@ static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
     if ((rc = dev_upload(ctx, &d_owner, owner))) return rc;
     if ((rc = dev_upload(ctx, &d_neigh, neigh))) return rc;
     if ((rc = dev_upload(ctx, &d_bc, bc))) return rc;
-    if ((rc = dev_upload(ctx, &d_area, std::vector<double>(d->area, d->area + nf)))) return rc;
+    const std::vector<double> area(d->area, d->area + nf), volume(d->volume, d->volume + nc);
+    if ((rc = dev_upload(ctx, &d_area, area))) return rc;
     if ((rc = dev_upload(ctx, &d_normal, normal))) return rc;
-    if ((rc = dev_upload(ctx, &d_vol, std::vector<double>(d->volume, d->volume + nc)))) return rc;
+    if ((rc = dev_upload(ctx, &d_vol, volume))) return rc;
     if ((rc = dev_upload(ctx, &d_solved, solved))) return rc;
     if ((rc = dev_upload(ctx, &d_update, update))) return rc;
     g.cf_ptr = d_ptr; g.cf_ent = d_ent; g.f_owner = d_owner; g.f_neigh = d_neigh; g.f_bc = d_bc;
