@@ -94,6 +94,25 @@ __device__ __forceinline__ void derive_cell(const double *c, const DivConsts &dc
     q.a = sqrt(GAMMA * T);
 }
 
+// derive_cell with the reciprocals of rho and rho*rho -- the root of every dependency chain of a cell --
+// supplied by the caller, who can start them as soon as rho is known (same operations, same bits)
+__device__ __forceinline__ void derive_cell_pre(const double *c, const double y, const double yrr, const DivConsts &dc, CellPrim &q)
+{
+    const double rho = c[FID_RHO];
+    const double rr  = rho * rho;
+    const double K = div_nr(c[FID_RHO_U] * c[FID_RHO_U] + c[FID_RHO_V] * c[FID_RHO_V] + c[FID_RHO_W] * c[FID_RHO_W], rr, yrr);
+    const double T = div_nr(div_nr(2.0 * c[FID_RHO_E], rho, y) - K, TWO_OVER_GM1, dc.y_c1);
+    q.rho = rho;
+    q.u = div_nr(c[FID_RHO_U], rho, y);
+    q.v = div_nr(c[FID_RHO_V], rho, y);
+    q.w = div_nr(c[FID_RHO_W], rho, y);
+    q.p = rho * T;
+    const double vel2 = q.u * q.u + q.v * q.v + q.w * q.w;
+    const double eto  = div_nr(q.p, GM1, dc.y_gm1) + 0.5 * rho * vel2;
+    q.H = eto + q.p;
+    q.a = sqrt(GAMMA * T);
+}
+
 // evalFluxes with n = +e_AXIS (src/euler.cpp:105-112): u*1 + v*0 + w*0 == u and p*0 == +0 exactly
 template <int AXIS>
 __device__ __forceinline__ void axis_flux(const CellPrim &q, double *F, double &lam)

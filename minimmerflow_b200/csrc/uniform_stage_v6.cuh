@@ -34,6 +34,9 @@
 #ifndef MMF_V6_LATE_UN
 #define MMF_V6_LATE_UN 1
 #endif
+#ifndef MMF_V6_EARLY_RCP
+#define MMF_V6_EARLY_RCP 0
+#endif
 
 namespace mmf {
 
@@ -298,6 +301,11 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pS[k] = 0.0; pUn[k] = 0.0; }
         }
+        // EARLY_RCP: 1/rho and 1/rho^2 of a plane -- the root of all its dependency chains -- are started one
+        // plane early, as soon as the prefetched rho is there (4 more registers across the loop edge)
+        constexpr bool EARLY_RCP = MMF_V6_EARLY_RCP;
+        double ny = 0.0, nyrr = 0.0;
+        if (EARLY_RCP) { ny = rcp_nr(nxt[FID_RHO]); nyrr = rcp_nr(nxt[FID_RHO] * nxt[FID_RHO]); }
 
         // one plane; the slot (= plane parity) arrives as a compile-time constant so that the slot offsets
         // fold into the shared-memory addresses
@@ -323,7 +331,14 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
             unp += plane;
 
             CellPrim q;
-            derive_cell(cU, dc, q);
+            if (EARLY_RCP) {
+                derive_cell_pre(cU, ny, nyrr, dc, q);
+                // the reciprocals the NEXT plane starts from, off its critical path (its rho was prefetched above)
+                ny   = rcp_nr(nxt[FID_RHO]);
+                nyrr = rcp_nr(nxt[FID_RHO] * nxt[FID_RHO]);
+            } else {
+                derive_cell(cU, dc, q);
+            }
 
             // ---- y record for row+1.  The slot held record it-2; row+1 read it before it published flux
             //      it-2, and this row took that flux during plane it-1 (or it-2): free. -------------------
@@ -466,7 +481,8 @@ uniform_stage_kernel_v6(const UniformGeom g, const double *__restrict__ Sin, con
                 for (int k = 0; k < NF; ++k) pUn[k] = unp[k * fs];
             }
             CellPrim q;
-            derive_cell(nxt, dc, q);
+            if (EARLY_RCP) derive_cell_pre(nxt, ny, nyrr, dc, q);
+            else           derive_cell(nxt, dc, q);
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
             const double lam = llf_area_flux(pU, pFz, plz, nxt, cFz, clz, Ah, AFz);

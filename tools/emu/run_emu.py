@@ -24,7 +24,7 @@ import oracle_lib  # noqa: E402
 from common import bits_equal, lexicographic_box_mesh  # noqa: E402
 
 CSRC = os.path.join(ROOT, "minimmerflow_b200", "csrc")
-LIB = os.path.join(HERE, "build", "libmmf_emu.so")
+LIB = os.environ.get("MMF_EMU_LIB") or os.path.join(HERE, "build", "libmmf_emu.so")
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int)
 
@@ -40,6 +40,8 @@ def build(force=False):
            "-o", LIB, os.path.join(HERE, "emu_stage.cpp")]
     if os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
         cmd.insert(1, "-DMMF_EMU_HAVE_V6")
+    # kernel build options under test, e.g. MMF_EMU_CXXFLAGS="-DMMF_V6_EARLY_RCP=1" (use with MMF_EMU_LIB=<other file>)
+    cmd[1:1] = os.environ.get("MMF_EMU_CXXFLAGS", "").split()
     subprocess.run(cmd, check=True)
 
 
