@@ -107,6 +107,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def stage_kernel_label():
+    """Name of the kernel that runs stages 2 and 3 (the dominant one), from the same knob the library reads."""
+    names = {"p": "uniform_stage_kernel_v5", "r": "uniform_stage_kernel_v5r", "d": "uniform_stage_kernel_v6",
+             "h": "uniform_stage_kernel_v6 (merged halo warp)", "3": "uniform_stage_kernel_v3"}
+    shapes = ["p16", "p16", "r12", "r12"]                      # library defaults (uniform_path.cuh)
+    cfg = [c for c in os.environ.get("MMF_STAGE_CFG", "").split(":") if c]
+    if len(cfg) == 1:
+        shapes = cfg * 4
+    else:
+        shapes[:len(cfg)] = cfg[:4]
+    s2, s3 = shapes[2], shapes[3]
+    label = f"{names.get(s2[0], s2[0])}<2>, {s2[1:] or '12'} warps"
+    if s3 != s2:
+        label += f" / {names.get(s3[0], s3[0])}<3>, {s3[1:] or '12'} warps"
+    else:
+        label = label.replace("<2>", "<2|3>")
+    return label + " (stages 2 and 3: two of the three launches of an RK3 step)"
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -353,7 +372,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src,
-                         "kernel": "uniform_stage_kernel_v5r<2|3> (stages 2 and 3: two of the three launches of an RK3 step)",
+                         "kernel": stage_kernel_label(),
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE[1] * cells_local,
                          "avg_launch_ms": dom_ms,
                          "stage_ms": stage_ms, "stage_GBps": stage_gbs,
