@@ -1,5 +1,5 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<p|r|d|t|h> -DMMF_TU_FORM_ID=<0..4> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<p|r|d|t|h|w> -DMMF_TU_FORM_ID=<0..5> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 #include "uniform_launch.cuh"
 
@@ -17,8 +17,10 @@
 #include "uniform_stage_v6.cuh"
 #elif MMF_TU_FORM_ID == 3
 #include "uniform_stage_v3.cuh"
+#elif MMF_TU_FORM_ID == 5
+#include "uniform_stage_v7.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t) or 4 (h)"
+#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t), 4 (h) or 5 (w)"
 #endif
 
 namespace mmf {
@@ -33,6 +35,14 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
 #else
     const bool xgk = uniform_use_xghost(ctx);
+#if MMF_TU_FORM_ID == 5
+    // two rows per warp: ports = warps + 1, the shared-memory layout of the merged-halo v6 kernel
+#define MMF_LAUNCH(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v7<STAGE, ORDER, NWV, XGV>, STAGE, NWV, stage_v6_smem_bytes(NWV, true), Sin, Un, Out, d_max)
+    if (sh.nw == 12) { if (xgk) MMF_LAUNCH(12, true); MMF_LAUNCH(12, false); }
+    if (xgk) MMF_LAUNCH(8, true);
+    MMF_LAUNCH(8, false);
+#undef MMF_LAUNCH
+#else
     // v5 forms: record (11) + flux (5) doubles per lane and row, two mbarriers per row; v6: twice that
 #if MMF_TU_FORM_ID == 2 || MMF_TU_FORM_ID == 4
 #define MMF_MH (MMF_TU_FORM_ID == 4)
@@ -51,6 +61,7 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     if (xgk) MMF_LAUNCH(12, true);
     MMF_LAUNCH(12, false);
 #undef MMF_LAUNCH
+#endif
 #endif
 }
 

@@ -17,14 +17,16 @@ namespace mmf {
 //   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
 //   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
 //       has been measured on the GPU), 'h' the same with ONE warp serving both halo rows (a CTA updates
-//       nw-1 rows instead of nw-2; opt-in likewise), '3' the older high-face kernel (uniform_stage_v3.cuh, 12 warps),
-//       kept as an independent cross-check
+//       nw-1 rows instead of nw-2; opt-in likewise), 'w' the merged-halo decoupled kernel with TWO y rows per
+//       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 or 12 warps; opt-in likewise), '3' the older
+//       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check
 struct StageShape {
     char form = 'p';
     int nw = 16;
     int lz = 0; // planes per CTA
-    // y rows a CTA updates: all warps but the two halo rows; form 'h' serves both halo rows with one warp
-    int rows() const { return form == 'h' ? nw - 1 : nw - 2; }
+    // y rows a CTA updates: all warps but the two halo rows; forms 'h' and 'w' serve both halo rows with
+    // one warp, and every other warp of form 'w' owns two rows
+    int rows() const { return form == 'w' ? 2 * (nw - 1) : form == 'h' ? nw - 1 : nw - 2; }
 };
 
 struct UniformPath {
@@ -76,7 +78,10 @@ static bool uniform_use_xghost(const mmf_ctx *ctx)
     const UniformPath *u = ctx->uni;
     if (!(ctx->comm && u->p2p && u->halo_inkernel && u->xghost)) return false;
     if (u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0) return false;
-    for (int st = 0; st < 4; ++st) if (u->shape[st].nw != 12 && u->shape[st].nw != 16) return false;
+    for (int st = 0; st < 4; ++st) {
+        const StageShape &sh = u->shape[st];
+        if (sh.form == 'w' ? (sh.nw != 8 && sh.nw != 12) : (sh.nw != 12 && sh.nw != 16)) return false;
+    }
     return true;
 }
 
@@ -187,19 +192,21 @@ MMF_DECLARE_STAGE_TUS(r)  // uniform_stage_v5r.cuh
 MMF_DECLARE_STAGE_TUS(d)  // uniform_stage_v6.cuh
 MMF_DECLARE_STAGE_TUS(h)  // uniform_stage_v6.cuh, one warp for both halo rows
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_v3.cuh (form '3')
+MMF_DECLARE_STAGE_TUS(w)  // uniform_stage_v7.cuh, two y rows per warp
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('p', 'r', 'd', 'h', '3') for a stage
+// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[5][4] = {
+    static const StageLauncher tab[6][4] = {
         { launch_stage_p_0, launch_stage_p_1, launch_stage_p_2, launch_stage_p_3 },
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
         { launch_stage_d_0, launch_stage_d_1, launch_stage_d_2, launch_stage_d_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
         { launch_stage_h_0, launch_stage_h_1, launch_stage_h_2, launch_stage_h_3 },
+        { launch_stage_w_0, launch_stage_w_1, launch_stage_w_2, launch_stage_w_3 },
     };
-    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : 0;
+    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : 0;
     return tab[f][stage];
 }
 

@@ -123,7 +123,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (164-166
     // registers, no spills) the fastest for stages 2 and 3, which also stream U^n.
     // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "d12" = the decoupled form
-    // everywhere, "h12" = decoupled with a merged halo warp, "312" = v3 everywhere.
+    // everywhere, "h12" = decoupled with a merged halo warp, "w8" = two y rows per warp, "312" = v3 everywhere.
     const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
     for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
@@ -135,8 +135,9 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != 'h' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != 'h' && sh.form != 'w' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
+            if (sh.form == 'w' && sh.nw == 16) break; // two rows per warp: 8 or 12 warps
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }

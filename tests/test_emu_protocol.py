@@ -24,7 +24,7 @@ def emu():
     return run_emu.load()
 
 
-@pytest.mark.parametrize("form", ["p", "r", "d", "h"])
+@pytest.mark.parametrize("form", ["p", "r", "d", "h", "w"])
 @pytest.mark.parametrize("chaos", [0, 300])
 def test_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, form, chaos):
     # Morton cube (the reference's numbering), z chunks of 6 planes: general and steady-state bodies
@@ -55,7 +55,7 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
     U0 = oracle.init_state(m)
     ref, ref_eig = oracle.compute_rhs(m, U0)
     out = {}
-    for form in ("r", "d", "h"):
+    for form in ("r", "d", "h", "w"):
         box = run_emu.Box(emu, oracle, dict(m), 2)
         U, R = box.new_array(), box.new_array()
         box.scatter(U, U0)
@@ -63,11 +63,11 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
         eig, _ = box.stage(form, 0, 8, 5, U, U, R, 0.0, 200, 5)
         assert eig == ref_eig
         out[form] = box.gather(R)
-    assert np.array_equal(out["r"], out["d"]) and np.array_equal(out["r"], out["h"])
+    assert all(np.array_equal(out["r"], out[f]) for f in ("d", "h", "w"))
     assert np.abs(out["d"] - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("form", ["r", "d", "h"])
+@pytest.mark.parametrize("form", ["r", "d", "h", "w"])
 def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
     """Multi-GPU layout of an x partition side (XGhost): the halo lanes i = -1 / i = nx take their column
     from compact arrays [field][k+1][j+1] instead of the padded array.  Here the columns hold the

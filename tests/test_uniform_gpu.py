@@ -59,13 +59,14 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
         assert eig == ref_eig and bits_equal(got, ref), problem
 
 
-# Stage-kernel forms that have not been measured on the GPU yet ('d', 'h' = uniform_stage_v6.cuh, checked on
-# the CPU emulator of tools/emu only): opt-in, so that an unproven kernel can never turn the suite red.
+# Stage-kernel forms that have not been measured on the GPU yet ('d', 'h' = uniform_stage_v6.cuh, 'w' =
+# uniform_stage_v7.cuh, checked on the CPU emulator of tools/emu only): opt-in, so that an unproven kernel can never turn the suite red.
 # MMF_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k fused_steps   is the first thing to run on them.
 EXPERIMENTAL = os.environ.get("MMF_TEST_EXPERIMENTAL", "0") not in ("", "0")
 _exp = pytest.mark.skipif(not EXPERIMENTAL, reason="experimental stage-kernel form: set MMF_TEST_EXPERIMENTAL=1")
 EXPERIMENTAL_CFGS = [pytest.param(c, marks=_exp) for c in ("d12", "d16", "d8", "p16:d16:d12:d12", "d8:r12:d16:p8",
-                                                            "h12", "h16", "h8", "p16:h16:h12:h12", "h8:d12:h16:r8")]
+                                                            "h12", "h16", "h8", "p16:h16:h12:h12", "h8:d12:h16:r8",
+                                                            "w8", "p16:w8:w8:w8", "w8:h12:w8:r12")]
 
 
 @pytest.mark.parametrize("lz", ["5", "1", "2"])
@@ -73,7 +74,7 @@ EXPERIMENTAL_CFGS = [pytest.param(c, marks=_exp) for c in ("d12", "d16", "d8", "
 def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
     """Every stage-kernel form and CTA shape (default mix first), ragged z chunks; one- and two-plane
     chunks for the forms that carry state from plane to plane."""
-    if lz != "5" and "d" not in cfg and "h" not in cfg:
+    if lz != "5" and "d" not in cfg and "h" not in cfg and "w" not in cfg:
         pytest.skip("one- and two-plane z chunks: the plane-decoupled forms only")
     if cfg:
         monkeypatch.setenv("MMF_STAGE_CFG", cfg)

@@ -43,6 +43,7 @@ inline void mbar_wait(unsigned long long *bar, unsigned parity)
 }
 
 inline double rcp_nr(double b) { return 1.0 / b; }
+inline void rcp_nr2(double a, double b, double &ya, double &yb) { ya = 1.0 / a; yb = 1.0 / b; }
 inline double div_nr(double a, double b, double) { return a / b; }
 
 inline float rcp_approx_f32(float x) { return 1.0f / x; }

@@ -163,6 +163,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 #include "uniform_stage_v5r.cuh"
 #ifdef MMF_EMU_HAVE_V6
 #include "uniform_stage_v6.cuh"
+#include "uniform_stage_v7.cuh"
 #endif
 
 namespace {
@@ -192,6 +193,7 @@ std::function<void()> bind_kernel_xg(int form, const Args &a)
 #ifdef MMF_EMU_HAVE_V6
     case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
 #endif
     default: return nullptr;
     }
@@ -207,6 +209,7 @@ std::function<void()> bind_kernel(int form, const Args &a)
 #ifdef MMF_EMU_HAVE_V6
     case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
 #endif
     default: return nullptr;
     }
@@ -283,7 +286,7 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     a.max_eig = max_eig;
     a.lz = lz;
     a.cta_est = cta_est;
-    const int rows = (form == 'h') ? nw - 1 : nw - 2; // rows a tile updates
+    const int rows = (form == 'w') ? 2 * (nw - 1) : (form == 'h') ? nw - 1 : nw - 2; // rows a tile updates
     const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + rows - 1) / rows, gz = (g.nz + lz - 1) / lz;
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;

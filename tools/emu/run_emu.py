@@ -57,6 +57,11 @@ def load():
     return lib
 
 
+def tile_rows(form, nw):
+    """y rows a CTA of nw warps updates (StageShape::rows in uniform_launch.cuh)."""
+    return 2 * (nw - 1) if form == "w" else nw - 1 if form == "h" else nw - 2
+
+
 def ia(v):
     return np.ascontiguousarray(v, dtype=np.int32)
 
@@ -146,8 +151,8 @@ class Box:
         return lo, hi, fs, pitch
 
     def smem_doubles(self, form, nw):
-        if form in ("d", "h"):
-            nr = nw + (1 if form == "h" else 0)   # merged halo: one more (virtual) row
+        if form in ("d", "h", "w"):
+            nr = nw + (1 if form in ("h", "w") else 0)   # merged halo: one more (virtual) row
             return nr * 2 * 16 * 32 + 4 * nr      # double-buffered records and fluxes, two mbarriers per slot and row
         return nw * 16 * 32 + 2 * nw
 
@@ -155,7 +160,7 @@ class Box:
         m = self.m
         me = np.zeros(1)
         nx, ny, nz = (int(v) for v in self.dims)
-        rows = nw - 1 if form == "h" else nw - 2
+        rows = tile_rows(form, nw)
         ntiles = ((nx + 29) // 30) * ((ny + rows - 1) // rows) * ((nz + lz - 1) // lz)
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
@@ -214,7 +219,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
             break
         # stage 3's FP32 estimate per TILE (what uniform_eig_select/tiles_kernel work from) must match the
         # largest cell eigenvalue max_d|u_d| + a of exactly that tile's cells
-        rows = nw - 1 if form == "h" else nw - 2
+        rows = tile_rows(form, nw)
         nx, ny, nz = (int(v) for v in box.dims)
         tx, ty = (nx + 29) // 30, (ny + rows - 1) // rows
         rho = Uo[:, 0]; vel = Uo[:, 1:4] / rho[:, None]
@@ -233,7 +238,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="p,r,d,h")
+    ap.add_argument("--forms", default="p,r,d,h,w")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -244,7 +249,7 @@ def main():
     oracle = oracle_lib.load()
     forms = [f for f in args.forms.split(",") if f]
     if not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        forms = [f for f in forms if f not in ("d", "h")]
+        forms = [f for f in forms if f not in ("d", "h", "w")]
     cases = []
     m = oracle.problem_mesh("vortex_xy", 3, 16)
     cases.append(("vortex 16^3 morton", m, 0, 6))

@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 export MMF_TEST_EXPERIMENTAL=1
-# 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp), bounded
+# 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp, w = + two y rows per warp), bounded
 timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps" > gpurun_out/experimental_parity.log 2>&1
 echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
 tail -5 gpurun_out/experimental_parity.log
@@ -15,7 +15,7 @@ timeout 600 python tools/stage_sweep.py --size 256 --steps 6 > gpurun_out/stage_
 cat gpurun_out/stage_sweep_256.jsonl
 # 3. z-chunk sensitivity of the two most promising mixes
 for lz in 26 32 43 52 64; do
-  timeout 300 python tools/stage_sweep.py --size 256 --steps 6 --variants "p16:p16:h12:h12@$lz,p16:p16:d12:d12@$lz,p16:p16:r12:r12@$lz" >> gpurun_out/stage_sweep_lz.jsonl 2>> gpurun_out/stage_sweep_256.err
+  timeout 300 python tools/stage_sweep.py --size 256 --steps 6 --variants "p16:p16:h12:h12@$lz,p16:p16:w8:w8@$lz,p16:p16:d12:d12@$lz,p16:p16:r12:r12@$lz" >> gpurun_out/stage_sweep_lz.jsonl 2>> gpurun_out/stage_sweep_256.err
 done
 cat gpurun_out/stage_sweep_lz.jsonl
 timeout 600 python tools/generic_bench.py --size 128 --steps 6 > gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err; cat gpurun_out/generic_bench_128.jsonl

@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--variants", default="p16:p16:r12:r12,p16:p16:d12:d12,p16:p16:h12:h12,p16:h16:h12:h12,h12,h16,d12,d16,p12,r12,p16,r16,312")
+    ap.add_argument("--variants", default="p16:p16:r12:r12,p16:p16:d12:d12,p16:p16:h12:h12,p16:h16:h12:h12,p16:p16:w8:w8,p16:w8:w8:w8,w8,h12,h16,d12,d16,p12,r12,p16,r16,312")
     args = ap.parse_args()
     U, h = vortex(args.size)
     cells = args.size ** 3
