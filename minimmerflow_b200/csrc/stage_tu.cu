@@ -36,9 +36,10 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 #else
     const bool xgk = uniform_use_xghost(ctx);
 #if MMF_TU_FORM_ID == 5
+    (void) sh;
     // two rows per warp: ports = warps + 1, the shared-memory layout of the merged-halo v6 kernel
 #define MMF_LAUNCH(NWV, XGV) return launch_stage_k(ctx, uniform_stage_kernel_v7<STAGE, ORDER, NWV, XGV>, STAGE, NWV, stage_v6_smem_bytes(NWV, true), Sin, Un, Out, d_max)
-    if (sh.nw == 12) { if (xgk) MMF_LAUNCH(12, true); MMF_LAUNCH(12, false); }
+    // 8 warps only: at 12 warps (168 registers) the two-cell body spills about 1 KB per thread
     if (xgk) MMF_LAUNCH(8, true);
     MMF_LAUNCH(8, false);
 #undef MMF_LAUNCH

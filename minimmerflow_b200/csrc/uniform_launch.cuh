@@ -18,7 +18,7 @@ namespace mmf {
 //   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
 //       has been measured on the GPU), 'h' the same with ONE warp serving both halo rows (a CTA updates
 //       nw-1 rows instead of nw-2; opt-in likewise), 'w' the merged-halo decoupled kernel with TWO y rows per
-//       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 or 12 warps; opt-in likewise), '3' the older
+//       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 warps; opt-in likewise), '3' the older
 //       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check
 struct StageShape {
     char form = 'p';
@@ -80,7 +80,7 @@ static bool uniform_use_xghost(const mmf_ctx *ctx)
     if (u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0) return false;
     for (int st = 0; st < 4; ++st) {
         const StageShape &sh = u->shape[st];
-        if (sh.form == 'w' ? (sh.nw != 8 && sh.nw != 12) : (sh.nw != 12 && sh.nw != 16)) return false;
+        if (sh.form == 'w' ? sh.nw != 8 : (sh.nw != 12 && sh.nw != 16)) return false;
     }
     return true;
 }

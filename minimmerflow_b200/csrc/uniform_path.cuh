@@ -137,7 +137,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             if (*p == ':') ++p;
             if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != 'h' && sh.form != 'w' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             if (sh.form == '3') sh.nw = 12;
-            if (sh.form == 'w' && sh.nw == 16) break; // two rows per warp: 8 or 12 warps
+            if (sh.form == 'w') sh.nw = 8;  // two rows per warp: 8 warps at 248 registers
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }

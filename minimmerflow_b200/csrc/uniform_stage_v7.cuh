@@ -12,7 +12,7 @@
 //     operations and shared-memory traffic per cell;
 //   * one halo warp serves both halo rows of the tile, as in form 'h'.
 // Per value the sequence of IEEE operations is the one of v5/v6 (same helpers, same accumulation order):
-// bit-identical to the oracle, checked on the CPU emulator (tools/emu) before any GPU time.
+// bit-identical results, checked on the CPU emulator (tools/emu) before any GPU time.
 //
 // Exchange between warps ("port" p = warp index; port 0 / NW belong to the halo warp), double buffered by
 // plane parity with one mbarrier per slot and port exactly as in v6:
