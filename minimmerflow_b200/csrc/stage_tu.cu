@@ -1,5 +1,5 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<p|r|d|t|h|w> -DMMF_TU_FORM_ID=<0..5> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<p|r|d|t|h|w|b> -DMMF_TU_FORM_ID=<0..6> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 #include "uniform_launch.cuh"
 
@@ -19,8 +19,10 @@
 #include "uniform_stage_v3.cuh"
 #elif MMF_TU_FORM_ID == 5
 #include "uniform_stage_v7.cuh"
+#elif MMF_TU_FORM_ID == 6
+#include "uniform_stage_v5rb.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t), 4 (h) or 5 (w)"
+#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t), 4 (h), 5 (w) or 6 (b)"
 #endif
 
 namespace mmf {
@@ -33,6 +35,9 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 #if MMF_TU_FORM_ID == 3
     (void) sh;
     return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
+#elif MMF_TU_FORM_ID == 6
+    (void) sh;
+    return launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
 #else
     const bool xgk = uniform_use_xghost(ctx);
 #if MMF_TU_FORM_ID == 5

@@ -152,4 +152,48 @@ __device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0x
 // ORDER: interface numbering convention deciding the per-cell accumulation order (NUM_*).
 constexpr int XW = 30; // cells updated per warp row (32-lane window, 2 overlap)
 
+// ---- a box with bodies: what one cell contributes to the max eigenvalue over the processed interfaces --------
+// (uniform_eig_body_kernel in uniform_kernels.cuh explains; solid = one flag per padded cell, 1 = not solved)
+__device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const double *__restrict__ Sin,
+                                                const unsigned char *__restrict__ solid, const int i, const int j, const int k)
+{
+    const long long o = uoff(g, i, j, k);
+    if (solid[o]) return 0.0;
+    DivConsts dc;
+    dc.y_gm1 = rcp_nr(GM1); dc.y_c1 = rcp_nr(TWO_OVER_GM1); dc.y_vol = 0.0;
+    double c[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) c[f] = Sin[f * g.fs + o];
+    CellPrim pr;
+    derive_cell(c, dc, pr);
+    double lmax = fmax(fmax(fabs(pr.u), fabs(pr.v)), fabs(pr.w)) + pr.a;
+    const int ijk[3] = { i, j, k }, ext[3] = { g.nx, g.ny, g.nz };
+    const long long step[3] = { 1, g.px, (long long) g.py * g.px };
+    for (int side = 0; side < 6; ++side) {
+        const int axis = side >> 1;
+        const bool hi = side & 1;
+        const long long on = hi ? o + step[axis] : o - step[axis];
+        const bool border = hi ? (ijk[axis] == ext[axis] - 1) : (ijk[axis] == 0);
+        double v[NF];
+        if (border) {
+            // the ghost cell holds the boundary condition's virtual state; a free-flow ghost is a copy
+            if (g.bc[side] == BC_FREE_FLOW || g.bc[side] < 0) continue;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) v[f] = Sin[f * g.fs + on];
+        } else {
+            if (!solid[on]) continue;
+            // wall: interface normal +e_axis with the low cell as owner; the BC sees it from the fluid side
+            double bn[3] = { 0.0, 0.0, 0.0 };
+            bn[axis] = 1.0;
+            if (!hi) { bn[0] = -1. * bn[0]; bn[1] = -1. * bn[1]; bn[2] = -1. * bn[2]; }
+            interface_bc_values(BC_WALL, bn, nullptr, c, v);
+        }
+        CellPrim pv;
+        derive_cell(v, dc, pv);
+        const double lam = fabs(axis == 0 ? pv.u : axis == 1 ? pv.v : pv.w) + pv.a;
+        lmax = (lam < lmax) ? lmax : lam;
+    }
+    return lmax;
+}
+
 } // namespace mmf

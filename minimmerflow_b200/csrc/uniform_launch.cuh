@@ -19,7 +19,9 @@ namespace mmf {
 //       has been measured on the GPU), 'h' the same with ONE warp serving both halo rows (a CTA updates
 //       nw-1 rows instead of nw-2; opt-in likewise), 'w' the merged-halo decoupled kernel with TWO y rows per
 //       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 warps; opt-in likewise), '3' the older
-//       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check
+//       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check, 'b' the rotate
+//       form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never by
+//       MMF_STAGE_CFG)
 struct StageShape {
     char form = 'p';
     int nw = 16;
@@ -27,6 +29,8 @@ struct StageShape {
     // y rows a CTA updates: all warps but the two halo rows; forms 'h' and 'w' serve both halo rows with
     // one warp, and every other warp of form 'w' owns two rows
     int rows() const { return form == 'w' ? 2 * (nw - 1) : form == 'h' ? nw - 1 : nw - 2; }
+    StageShape() = default;
+    StageShape(char f, int n) : form(f), nw(n) {}
 };
 
 struct UniformPath {
@@ -43,6 +47,10 @@ struct UniformPath {
     int n_tiles3 = 0;
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
     bool clamp_ff = true;             // no stage runs the v3 form: free-flow ghosts are never read
+    // bodies (opt-in, MMF_UNIFORM_BODIES=1): one flag per padded cell, 1 = not solved (src/main.cpp:221-237);
+    // the ghost shell repeats the flag of the cell it touches
+    unsigned char *solid = nullptr;
+    bool bodies = false;              // set before the arrays are laid out: selects kernel form 'b' for every stage
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
     // direct peer stores over NVLink (comm.cuh): the neighbours' state arrays and arrival flags,
@@ -176,6 +184,28 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, 
     return MMF_OK;
 }
 
+// form 'b' (a box with bodies, single GPU): the 12-warp rotate-form geometry plus the flag array
+template <typename K>
+static int launch_stage_body(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    const int nw = 12, lz = u->shape[stage].lz, rows = u->shape[stage].rows();
+    if (!u->solid) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'b' needs the flag array of a box with bodies");
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
+    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
+    HaloWait hw{};
+    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
+                                                   uniform_load_clamp(u), hw, u->solid);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
 // ---- per (form, stage) launchers, defined in stage_tu.cu ----------------------------------------------
 // order = NUM_MORTON / NUM_LEXI / NUM_AXIS; CTA shape and z chunk come from ctx->uni->shape[stage]
 typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const double *Un, double *Out, double *d_max);
@@ -193,20 +223,22 @@ MMF_DECLARE_STAGE_TUS(d)  // uniform_stage_v6.cuh
 MMF_DECLARE_STAGE_TUS(h)  // uniform_stage_v6.cuh, one warp for both halo rows
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_v3.cuh (form '3')
 MMF_DECLARE_STAGE_TUS(w)  // uniform_stage_v7.cuh, two y rows per warp
+MMF_DECLARE_STAGE_TUS(b)  // uniform_stage_v5rb.cuh, a box with bodies
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3') for a stage
+// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3', 'b') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[6][4] = {
+    static const StageLauncher tab[7][4] = {
         { launch_stage_p_0, launch_stage_p_1, launch_stage_p_2, launch_stage_p_3 },
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
         { launch_stage_d_0, launch_stage_d_1, launch_stage_d_2, launch_stage_d_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
         { launch_stage_h_0, launch_stage_h_1, launch_stage_h_2, launch_stage_h_3 },
         { launch_stage_w_0, launch_stage_w_1, launch_stage_w_2, launch_stage_w_3 },
+        { launch_stage_b_0, launch_stage_b_1, launch_stage_b_2, launch_stage_b_3 },
     };
-    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : 0;
+    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : (form == 'b') ? 6 : 0;
     return tab[f][stage];
 }
 

@@ -142,6 +142,9 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }
     }
+    if (u->bodies) { // a box with bodies: the one kernel form that knows about them, whatever MMF_STAGE_CFG says
+        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'b', 12 };
+    }
     // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
     // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
     // derives for its first z interface; chunks stay between 16 and 96 planes.
@@ -253,8 +256,10 @@ static void predicted_face_order(int numbering, const int ijk[3], int order[6])
     }
 }
 
-// Decide whether a host mesh description is a full, conforming, uniform, all-solved 3-D box whose
-// interface numbering matches a known convention; if so build the uniform path from it.
+// Decide whether a host mesh description is a full, conforming, uniform 3-D box whose interface numbering
+// matches a known convention; if so build the uniform path from it.  All cells solved -- or, opt-in until the
+// kernel has run on the GPU (MMF_UNIFORM_BODIES=1), a box with bodies: cells that are not solved, and BC_WALL
+// on exactly the interfaces between a solved and an unsolved cell (src/main.cpp:221-237, 251-277).
 static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
 {
     *used = false;
@@ -270,7 +275,9 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
     if (nf != nf_expected) return MMF_OK;
     if (d->interface_order && d->n_interfaces_listed != nf) return MMF_OK;
 
-    // cells: a bijection onto the lattice, all solved and internal, one volume
+    // cells: a bijection onto the lattice, all internal, one volume; all solved unless bodies are allowed
+    const bool allow_bodies = getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) && !ctx->comm;
+    bool bodies = false;
     std::vector<int64_t> lattice_to_raw((size_t) nc, -1);
     const double V = d->volume[0];
     for (int64_t c = 0; c < nc; ++c) {
@@ -279,7 +286,11 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
         const int64_t l = ((int64_t) k * ny + j) * nx + i;
         if (lattice_to_raw[l] >= 0) return MMF_OK;
         lattice_to_raw[l] = c;
-        if (!d->solved[c] || (d->internal && !d->internal[c]) || d->volume[c] != V) return MMF_OK;
+        if ((d->internal && !d->internal[c]) || d->volume[c] != V) return MMF_OK;
+        if (!d->solved[c]) {
+            if (!allow_bodies) return MMF_OK;
+            bodies = true;
+        }
     }
     const double A = d->area[0];
     const double h = std::sqrt(A);
@@ -306,7 +317,8 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
             for (int e = 0; e < 3; ++e) {
                 if (ncell[e] - oc[e] != (e == axis ? sgn : 0)) return MMF_OK;
             }
-            if (d->bc[f] != MMF_BC_NONE) return MMF_OK;
+            const bool wall = (d->solved[o] != 0) != (d->solved[n] != 0);
+            if (d->bc[f] != (wall ? MMF_BC_WALL : MMF_BC_NONE)) return MMF_OK;
             const int so = 2 * axis + (sgn > 0 ? 1 : 0), sn = 2 * axis + (sgn > 0 ? 0 : 1);
             if (face_pos[o * 6 + so] >= 0 || face_pos[n * 6 + sn] >= 0) return MMF_OK;
             face_pos[o * 6 + so] = q;
@@ -358,9 +370,34 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
     memcpy(g.dirichlet, d->dirichlet_info, sizeof g.dirichlet);
     u->iface_numbering = numbering;
     u->order_exact = order_exact;
+    u->bodies = bodies;
     ctx->path = MMF_PATH_UNIFORM;
     int rc = uniform_alloc(ctx, u);
     if (rc) return rc;
+    if (bodies) {
+        // one flag per padded cell; the ghost shell repeats the cell it touches, so that the border interface of
+        // a cell that is not solved is skipped like the reference skips it (src/euler.cpp:181-183)
+        std::vector<unsigned char> flag((size_t) g.fs, 0);
+        for (int64_t c = 0; c < nc; ++c) {
+            if (!d->solved[c]) flag[(size_t) uoff(g, d->cell_ijk[3 * c], d->cell_ijk[3 * c + 1], d->cell_ijk[3 * c + 2])] = 1;
+        }
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j) {
+                flag[(size_t) uoff(g, -1, j, k)] = flag[(size_t) uoff(g, 0, j, k)];
+                flag[(size_t) uoff(g, nx, j, k)] = flag[(size_t) uoff(g, nx - 1, j, k)];
+            }
+        for (int k = 0; k < nz; ++k)
+            for (int i = 0; i < nx; ++i) {
+                flag[(size_t) uoff(g, i, -1, k)] = flag[(size_t) uoff(g, i, 0, k)];
+                flag[(size_t) uoff(g, i, ny, k)] = flag[(size_t) uoff(g, i, ny - 1, k)];
+            }
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                flag[(size_t) uoff(g, i, j, -1)] = flag[(size_t) uoff(g, i, j, 0)];
+                flag[(size_t) uoff(g, i, j, nz)] = flag[(size_t) uoff(g, i, j, nz - 1)];
+            }
+        if ((rc = dev_upload(ctx, &u->solid, flag))) return rc;
+    }
     std::vector<int> off((size_t) nc);
     for (int64_t c = 0; c < nc; ++c) {
         off[c] = (int) uoff(g, d->cell_ijk[3 * c], d->cell_ijk[3 * c + 1], d->cell_ijk[3 * c + 2]);
@@ -387,6 +424,13 @@ static int uniform_scatter_state(mmf_ctx *ctx, int field, const double *staging)
     uniform_scatter_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
         u->g, u->cell_numbering, u->cell_off, staging, S, ctx->n_cells);
     MMF_LAUNCH_CHECK(ctx);
+    if (u->bodies && field == MMF_FIELD_W) {
+        // the fused stages alternate between two work arrays and never write a cell that is not solved: such
+        // cells must hold the host's value in both
+        uniform_scatter_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
+            u->g, u->cell_numbering, u->cell_off, staging, u->arr[3 - u->w_cur], ctx->n_cells);
+        MMF_LAUNCH_CHECK(ctx);
+    }
     if (field == MMF_FIELD_U) u->eig_candidate = false;
     if (field != MMF_FIELD_RHS) return uniform_refresh_ghosts(ctx, S, 0);
     return MMF_OK;
@@ -424,9 +468,9 @@ static int uniform_rk(mmf_ctx *ctx, int stage)
     dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
     double *U = u->arr[0], *W = u->arr[u->w_cur], *R = u->arr[3];
     switch (stage) {
-    case 1: uniform_rk_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
-    case 2: uniform_rk_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
-    default: uniform_rk_kernel<3><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R); break;
+    case 1: uniform_rk_kernel<1><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R, u->solid); break;
+    case 2: uniform_rk_kernel<2><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R, u->solid); break;
+    default: uniform_rk_kernel<3><<<grid, 256, 0, ctx->stream>>>(g, ctx->d_ctl, U, W, R, u->solid); break;
     }
     MMF_LAUNCH_CHECK(ctx);
     if (stage == 3) u->eig_candidate = false;
@@ -450,7 +494,11 @@ static int uniform_step(mmf_ctx *ctx)
     trace_point(ctx, "gap");
     begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, u->eig_candidate ? 1 : 0);
     MMF_LAUNCH_CHECK(ctx);
-    if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass (+ all-reduce)
+    if (u->bodies) { // a box with bodies: a full pass every step (wall images have their own eigenvalue)
+        dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
+        uniform_eig_body_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, u->solid, &c->max_eig[0]);
+        MMF_LAUNCH_CHECK(ctx);
+    } else if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass (+ all-reduce)
         dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
         uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
         MMF_LAUNCH_CHECK(ctx);
@@ -475,7 +523,7 @@ static int uniform_step(mmf_ctx *ctx)
     trace_point(ctx, "stage3");
     u->w_cur = 2;
     const StageShape &s3 = u->shape[3];
-    if (s3.form != '3') {
+    if (s3.form != '3' && !u->bodies) {
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
         const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.rows() - 1) / s3.rows();

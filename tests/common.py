@@ -64,6 +64,24 @@ def lexicographic_box_mesh(nx, ny, nz, h, bc_code, origin=(0.0, 0.0, 0.0)):
                 internal=np.ones(nc, np.uint8), fluid=np.ones(nc, np.uint8), h=h)
 
 
+def with_bodies(m, boxes):
+    """Flags and BC table of a mesh with body boxes (xMin,yMin,zMin,xMax,yMax,zMax), set up the way
+    src/main.cpp:221-237, 251-277 does: cells whose centroid lies in a closed box are not solved, interfaces
+    between a solved and an unsolved cell get BC_WALL (2).  Border interfaces keep their code."""
+    m = dict(m)
+    cc = m["ccentroid"]
+    solid = np.zeros(cc.shape[0], bool)
+    for b in boxes:
+        solid |= np.all((cc >= np.array(b[:3])) & (cc <= np.array(b[3:])), axis=1)
+    fluid = (~solid).astype(np.uint8)
+    bc = m["bc"].copy()
+    inner = m["neigh"] >= 0
+    o, n = m["owner"][inner], m["neigh"][inner]
+    bc[inner] = np.where(fluid[o] != fluid[n], 2, -1)
+    m.update(fluid=fluid, solved=fluid.copy(), bc=bc)
+    return m
+
+
 def reference_cases():
     with open(os.path.join(HERE, "golden", "reference_cases.json")) as f:
         return json.load(f)["cases"]

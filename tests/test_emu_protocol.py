@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools", "emu"))
 
 import run_emu  # noqa: E402
-from common import lexicographic_box_mesh  # noqa: E402
+from common import lexicographic_box_mesh, with_bodies  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -93,3 +93,25 @@ def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
         emu.emu_set_xghost(None, None, 0, 0)
     assert eig == ref_eig
     assert np.array_equal(box.gather(R), ref)
+
+
+@pytest.mark.parametrize("chaos", [0, 300])
+def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, chaos):
+    """Kernel form 'b' (uniform_stage_v5rb.cuh): a uniform box with bodies -- unsolved cells, wall interfaces
+    evaluated against the fluid cell's mirror image, solid | solid interfaces skipped -- and the eigenvalue
+    pass that chooses dt there (eig_body_cell), bit for bit against the oracle."""
+    # the reference's set-up: Morton cube, reflecting borders, a box body inside
+    m = oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
+    assert (m["solved"] == 0).sum() > 50 and (m["bc"] == 2).sum() > 100
+    assert run_emu.check_case(emu, oracle, "radsod 16^3 + body", dict(m), 0, "b", 12, 6, 2, chaos, 1)
+    # ragged lexicographic box, free-flow borders (clamped loads), bodies touching the border, a one-cell
+    # body and a one-cell gap between two bodies; two-plane z chunks
+    m = with_bodies(lexicographic_box_mesh(33, 9, 5, 0.5, 0), [[-1, -1, -1, 1.2, 1.2, 1.2], [7.1, 2.1, 1.1, 7.4, 2.4, 1.4],
+                                                               [10.1, 0.0, 0.0, 11.9, 9.0, 1.4], [12.6, 0.0, 0.0, 16.4, 2.4, 9.0]])
+    m["problem"] = "vortex_xy"
+    assert (m["solved"] == 0).sum() > 30
+    assert run_emu.check_case(emu, oracle, "box 33x9x5 + bodies", dict(m), 1, "b", 12, 2, 2, chaos, 2)
+    # reflecting borders with a body on them
+    m = with_bodies(lexicographic_box_mesh(7, 23, 4, 0.5, 1), [[-1, 4.1, -1, 1.4, 6.4, 9.0], [2.1, 10.1, 0.6, 2.9, 11.4, 1.4]])
+    m["problem"] = "radsod"
+    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, "b", 8, 3, 2, chaos, 3)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff
+from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff, with_bodies
 
 pytestmark = pytest.mark.gpu
 
@@ -93,6 +93,65 @@ def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
             t += dto
         assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
         assert bits_equal(s.get_state(mmf.FIELD_W), Wo)
+
+
+def _body_meshes(oracle):
+    yield "radsod 32^3 + body", oracle.problem_mesh("radsod", 3, 32, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
+    yield "sod3d_x 16^3 + bodies at the border", oracle.problem_mesh(
+        "sod3d_x", 3, 16, boxes=[[-1.1, -1.1, -1.1, -0.6, -0.3, -0.8], [0.3, 0.1, 0.4, 1.1, 1.1, 1.1]])
+    m = with_bodies(lexicographic_box_mesh(37, 29, 11, 0.5, 1), [[-1, 4.1, -1, 1.4, 6.4, 9.0], [7.1, 2.1, 1.1, 7.4, 2.4, 1.4],
+                                                                [10.1, 0.0, 0.0, 11.9, 9.0, 1.4], [12.6, 0.0, 0.0, 16.4, 2.4, 9.0]])
+    m["problem"] = "radsod"
+    yield "box 37x29x11 + bodies", m
+
+
+def test_box_with_bodies_stays_on_the_generic_path_by_default(mmf, oracle, monkeypatch):
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
+    m = oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_GENERIC
+
+
+@_exp
+def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
+    """Kernel form 'b' (uniform_stage_v5rb.cuh, opt-in MMF_UNIFORM_BODIES=1; checked on the CPU emulator only so
+    far): a uniform box with bodies on the fused path -- RHS, the dt eigenvalue, ten fused steps and the unfused
+    operator sequence, bitwise against the oracle; cells that are not solved keep the host's values."""
+    monkeypatch.setenv("MMF_UNIFORM_BODIES", "1")
+    rng = np.random.default_rng(11)
+    for name, m in _body_meshes(oracle):
+        nc = m["volume"].shape[0]
+        if "origin" in m:
+            U = oracle.init_state(m)
+        else:
+            rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-0.4, 0.4, (nc, 3)); p = rng.uniform(0.6, 1.4, nc)
+            U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+        ref, ref_eig = oracle.compute_rhs(m, U)
+        W0 = U[::-1].copy()                      # what the host holds in W: must survive in the unsolved cells
+        Uo, Wo, Ro = U.copy(), W0.copy(), np.zeros_like(U)
+        with mmf.EulerSolver.from_mesh(m) as s:
+            assert s.info()["path"] == mmf.PATH_UNIFORM, name
+            s.set_state(mmf.FIELD_U, U)
+            s.set_state(mmf.FIELD_W, W0)
+            assert s.compute_rhs(mmf.FIELD_U) == ref_eig, name
+            assert bits_equal(s.get_state(mmf.FIELD_RHS), ref), name
+            t = 0.0
+            for _ in range(10):
+                dto, me3 = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+                dtg, meg = s.step(0.45, float(m["size"].min()), t, 1e30)
+                assert dtg == dto and list(me3) == meg, name
+                t += dto
+            assert bits_equal(s.get_state(mmf.FIELD_U), Uo), name
+            assert bits_equal(s.get_state(mmf.FIELD_W), Wo), name
+            # unfused operators on the same handle (src/main.cpp's own sequence)
+            R, me = oracle.compute_rhs(m, Uo)
+            assert s.compute_rhs(mmf.FIELD_U) == me, name
+            dt = oracle.choose_dt(0.45, float(m["size"].min()), me, 0.0, 4.0)
+            oracle.rk_stage(m, 1, dt, Uo, Wo, R); s.rk_stage(1, dt)
+            R, me = oracle.compute_rhs(m, Wo)
+            assert s.compute_rhs(mmf.FIELD_W) == me, name
+            oracle.rk_stage(m, 2, dt, Uo, Wo, R); s.rk_stage(2, dt)
+            assert bits_equal(s.get_state(mmf.FIELD_W), Wo), name
 
 
 def test_unfused_operator_sequence_on_uniform_path(mmf, oracle):

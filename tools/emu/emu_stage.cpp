@@ -164,6 +164,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 #ifdef MMF_EMU_HAVE_V6
 #include "uniform_stage_v6.cuh"
 #include "uniform_stage_v7.cuh"
+#include "uniform_stage_v5rb.cuh"
 #endif
 
 namespace {
@@ -181,6 +182,7 @@ struct Args {
     LoadClamp lc;
     HaloWait hw;
     XGhost xg;
+    const unsigned char *solid; // form 'b': flag array of a box with bodies
 };
 
 // compact x ghost columns (XG = true instantiations): the 12-warp shapes only, to bound the build time
@@ -210,6 +212,7 @@ std::function<void()> bind_kernel(int form, const Args &a)
     case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
+    case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
 #endif
     default: return nullptr;
     }
@@ -240,6 +243,7 @@ std::function<void()> bind_order(int order, int form, int nw, const Args &a)
 } // namespace
 
 static mmf::XGhost g_xghost{};
+static const unsigned char *g_solid = nullptr;
 
 extern "C" {
 
@@ -248,6 +252,9 @@ void emu_set_xghost(const double *lo, const double *hi, long long fs, int pitch)
 {
     g_xghost.lo = lo; g_xghost.hi = hi; g_xghost.fs = fs; g_xghost.pitch = pitch;
 }
+
+// flag array (padded layout of one field, 1 = not solved) for the NEXT emu_stage calls of form 'b'
+void emu_set_solid(const unsigned char *solid) { g_solid = solid; }
 
 // padded extents of a box, as uniform_alloc (uniform_path.cuh) lays them out
 void emu_padded(const int dims[3], int pad[3], long long *fs)
@@ -291,6 +298,7 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;
     a.xg = g_xghost;
+    a.solid = g_solid;
     if ((size_t) smem_doubles * sizeof(double) > sizeof(mmf::smem)) return -2;
 
     std::function<void()> body;
@@ -305,6 +313,26 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     emu::g_chaos = chaos;
     emu::launch(gx, gy, gz, nw * 32, mmf::smem, (size_t) smem_doubles * sizeof(double), body, seed);
     return 0;
+}
+
+// max eigenvalue over the processed interfaces of a box with bodies: eig_body_cell (the per-thread body of
+// uniform_eig_body_kernel) over all cells, plain loops
+double emu_eig_body(const int dims[3], const int bc[6], const double *Sin, const unsigned char *solid)
+{
+    UniformGeom g{};
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    int pad[3];
+    emu_padded(dims, pad, &g.fs);
+    g.px = pad[0]; g.py = pad[1]; g.pz = pad[2];
+    for (int s = 0; s < 6; ++s) g.bc[s] = bc[s];
+    double m = 0.0;
+    for (int k = 0; k < g.nz; ++k)
+        for (int j = 0; j < g.ny; ++j)
+            for (int i = 0; i < g.nx; ++i) {
+                const double l = eig_body_cell(g, Sin, solid, i, j, k);
+                m = (l < m) ? m : l;
+            }
+    return m;
 }
 
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }

@@ -54,12 +54,15 @@ def load():
                                               _D, _D, _D, C.c_double, _D, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_uint]
     lib.emu_set_spin_limit.argtypes = [C.c_longlong]
     lib.emu_set_xghost.argtypes = [_D, _D, C.c_longlong, C.c_int]
+    lib.emu_set_solid.argtypes = [C.c_void_p]
+    lib.emu_eig_body.restype = C.c_double
+    lib.emu_eig_body.argtypes = [_I, _I, _D, C.c_void_p]
     return lib
 
 
 def tile_rows(form, nw):
     """y rows a CTA of nw warps updates (StageShape::rows in uniform_launch.cuh)."""
-    return 2 * (nw - 1) if form == "w" else nw - 1 if form == "h" else nw - 2
+    return 2 * (nw - 1) if form == "w" else nw - 1 if form == "h" else nw - 2   # 'b': the rotate-form geometry
 
 
 def ia(v):
@@ -88,6 +91,20 @@ class Box:
         ff = [b == 0 for b in self.bc]
         self.clamp = ia([0 if ff[0] else -1, nx - 1 if ff[1] else nx, 0 if ff[2] else -1, ny - 1 if ff[3] else ny,
                          0 if ff[4] else -1, nz - 1 if ff[5] else nz])
+        # bodies: one flag per padded cell (1 = not solved), the ghost shell repeats the cell it touches
+        # (what uniform_try_create builds for kernel form 'b')
+        self.solid = None
+        if "solved" in m and not np.all(m["solved"]):
+            px, py, pz = (int(v) for v in pad)
+            inner = np.zeros((nz, ny, nx), np.uint8)
+            inner[self.ijk[:, 2], self.ijk[:, 1], self.ijk[:, 0]] = 1 - m["solved"].astype(np.uint8)
+            vol = np.zeros((pz, py, px), np.uint8)
+            vol[1:nz + 1, 1:ny + 1, 1:nx + 1] = inner
+            vol[0, :, :] = vol[1, :, :]; vol[nz + 1, :, :] = vol[nz, :, :]
+            vol[:, 0, :] = vol[:, 1, :]; vol[:, ny + 1, :] = vol[:, ny, :]
+            vol[:, :, 0] = vol[:, :, 1]; vol[:, :, nx + 1] = vol[:, :, nx]
+            self.solid = np.zeros(self.fs, np.uint8)
+            self.solid[:px * py * pz] = vol.reshape(-1)
 
     def new_array(self):
         a = np.empty((5, self.fs))
@@ -156,6 +173,11 @@ class Box:
             return nr * 2 * 16 * 32 + 4 * nr      # double-buffered records and fluxes, two mbarriers per slot and row
         return nw * 16 * 32 + 2 * nw
 
+    def eig_body(self, arr):
+        """uniform_eig_body_kernel: the max eigenvalue that chooses dt on a box with bodies."""
+        return self.lib.emu_eig_body(self.dims.ctypes.data_as(_I), ia(self.bc).ctypes.data_as(_I), arr.ctypes.data_as(_D),
+                                     self.solid.ctypes.data)
+
     def stage(self, form, stage, nw, lz, Sin, Un, Out, dt, chaos=0, seed=1):
         m = self.m
         me = np.zeros(1)
@@ -165,6 +187,9 @@ class Box:
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
         dirichlet = np.zeros(5)
+        if (self.solid is not None) != (form == "b"):
+            raise RuntimeError("kernel form 'b' is the one for a box with bodies, and only that")
+        self.lib.emu_set_solid(self.solid.ctypes.data if self.solid is not None else None)
         rc = self.lib.emu_stage(ord(form), stage, self.order, nw, lz, self.dims.ctypes.data_as(_I), zero3.ctypes.data_as(_I),
                                 self.dims.ctypes.data_as(_I), ia(self.bc).ctypes.data_as(_I), float(m["h"]),
                                 float(m["area"][0]), float(m["volume"][0]), dirichlet.ctypes.data_as(_D),
@@ -191,6 +216,8 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
     # RHS only
     ref_rhs, ref_eig = oracle.compute_rhs(m, U0)
     U = box.new_array(); Wa = box.new_array(); Wb = box.new_array(); R = box.new_array()
+    if box.solid is not None:
+        R[:] = 0.0   # uniform_ensure_rhs: solid cells keep the zero euler::computeRHS starts from
     box.scatter(U, U0)
     box.fill_ghosts(U)
     eig, _ = box.stage(form, 0, nw, lz, U, U, R, 0.0, chaos, seed)
@@ -204,6 +231,9 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
     t = 0.0
     for s in range(steps):
         dt, me3 = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+        if box.solid is not None and box.eig_body(U) != me3[0]:
+            ok = False
+            print(f"   step {s}: eigenvalue pass {box.eig_body(U)!r} vs stage-1 face maximum {me3[0]!r}")
         e1, _ = box.stage(form, 1, nw, lz, U, U, Wa, dt, chaos, seed + 10 * s + 1)
         box.fill_ghosts(Wa)
         e2, _ = box.stage(form, 2, nw, lz, Wa, U, Wb, dt, chaos, seed + 10 * s + 2)
@@ -227,18 +257,20 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
         lam = np.abs(vel).max(1) + np.sqrt(1.4 * pr / rho)
         tile = ((box.ijk[:, 2] // lz) * ty + box.ijk[:, 1] // rows) * tx + box.ijk[:, 0] // 30
         want = np.zeros(est.shape[0])
+        if box.solid is not None:
+            lam = np.where(m["solved"] != 0, lam, 0.0)   # solid cells are never written: no estimate
         np.maximum.at(want, tile, lam)
         if not np.allclose(est, want, rtol=2e-5, atol=0):
             ok = False
             bad = int((~np.isclose(est, want, rtol=2e-5, atol=0)).sum())
-            print(f"   step {s}: {bad} of {est.shape[0]} tile estimates off (max rel {np.abs(est / want - 1).max():.2e})")
+            print(f"   step {s}: {bad} of {est.shape[0]} tile estimates off (max rel {np.abs(est / np.maximum(want, 1e-300) - 1).max():.2e})")
     print(f"{'ok  ' if ok else 'FAIL'} {name:28s} form {form} nw {nw:2d} lz {lz:2d} order {order} chaos {chaos:3d}  ({time.time() - t0:.1f} s)")
     return ok
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="p,r,d,h,w")
+    ap.add_argument("--forms", default="p,r,d,h,w,b")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -249,7 +281,7 @@ def main():
     oracle = oracle_lib.load()
     forms = [f for f in args.forms.split(",") if f]
     if not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        forms = [f for f in forms if f not in ("d", "h", "w")]
+        forms = [f for f in forms if f not in ("d", "h", "w", "b")]
     cases = []
     m = oracle.problem_mesh("vortex_xy", 3, 16)
     cases.append(("vortex 16^3 morton", m, 0, 6))
@@ -259,8 +291,22 @@ def main():
         cases.append(("box 5x23x7 lexi reflecting", lexicographic_box_mesh(5, 23, 7, 0.5, 1), 1, 7))
         cases.append(("box 31x7x2 lexi free-flow", lexicographic_box_mesh(31, 7, 2, 0.5, 0), 1, 1))
         cases.append(("box 33x8x5 lexi reflecting", lexicographic_box_mesh(33, 8, 5, 0.5, 1), 1, 2))
+    # boxes with bodies (kernel form 'b' only): a box body off the Morton cube's centre, two bodies touching
+    # the border, a one-cell body
+    body_cases = []
+    if "b" in forms:
+        forms = [f for f in forms if f != "b"]
+        body_cases.append(("radsod 16^3 + box body", oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]]), 0, 6))
+        if not args.quick:
+            body_cases.append(("sod3d_x 16^3 + 2 bodies at the border", oracle.problem_mesh(
+                "sod3d_x", 3, 16, boxes=[[-1.1, -1.1, -1.1, -0.6, -0.3, -0.8], [0.3, 0.1, 0.4, 1.1, 1.1, 1.1]]), 0, 5))
+            body_cases.append(("vortex 16^3 + one-cell body", oracle.problem_mesh(
+                "vortex_xy", 3, 16, boxes=[[0.0, 0.0, 0.0, 0.6, 0.6, 0.6]]), 0, 16))
     all_ok = True
     for rep in range(args.repeat):
+        for name, mesh, order, lz in body_cases:
+            for nw in (int(x) for x in args.nw.split(",")):
+                all_ok &= check_case(lib, oracle, name, dict(mesh), order, "b", nw, lz, args.steps, args.chaos, 1 + 100 * rep)
         for name, mesh, order, lz in cases:
             for form in forms:
                 for nw in (int(x) for x in args.nw.split(",")):

@@ -28,6 +28,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __shared__
 #define __launch_bounds__(...)
 #define __maxnreg__(...)

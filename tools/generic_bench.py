@@ -5,6 +5,7 @@ Development tool (the number that tells how far the generic pa
 before it is optimised).  Needs a GPU:
 
     python tools/generic_bench.py --size 128 --steps 6
+    python tools/generic_bench.py --size 128 --steps 6 --bodies     # a box with bodies: form 'b' against the generic path
 """
 import argparse
 import json
@@ -25,9 +26,16 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--problem", default="vortex_xy")
+    ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain; the fused path then needs MMF_UNIFORM_BODIES=1")
     args = ap.parse_args()
     orc = oracle_lib.load()
-    m = orc.problem_mesh(args.problem, 3, args.size)
+    boxes = None
+    if args.bodies:
+        os.environ["MMF_UNIFORM_BODIES"] = "1"
+        _, origin, length = orc.domain(args.problem, 3)
+        lo = lambda f: [origin[e] + f[e] * length for e in range(3)]
+        boxes = [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))]
+    m = orc.problem_mesh(args.problem, 3, args.size, boxes=boxes)
     U = orc.init_state(m)
     cells = m["volume"].shape[0]
     out = {}
@@ -40,8 +48,9 @@ def main():
             s.run(0.45, m["h"], 0.0, 1e30, max_steps=args.steps)
             ms = s.timer_stop()
             out[name] = s.get_state(mmf.FIELD_U)
-            print(json.dumps({"path": name, "path_code": path, "cells": cells, "ms_per_step": ms / args.steps,
-                              "cell_updates_per_s": cells * 3 * args.steps / (ms * 1e-3)}), flush=True)
+            print(json.dumps({"path": name, "path_code": path, "cells": cells, "solved_cells": int(m["solved"].sum()),
+                              "ms_per_step": ms / args.steps,
+                              "cell_updates_per_s": int(m["solved"].sum()) * 3 * args.steps / (ms * 1e-3)}), flush=True)
     print(json.dumps({"bitwise_equal": bool(np.array_equal(out["uniform"], out["generic"]))}))
 
 

@@ -78,12 +78,12 @@ def loop_stats(body):
 
 
 def describe(name):
-    m = re.search(r"kernel_(v\d+r?)ILi(\d)ELi(\d)ELi(\d+)ELb([01])(?:ELb([01]))?", name)
+    m = re.search(r"kernel_(v\d+[a-z]*)ILi(\d)ELi(\d)ELi(\d+)E(?:Lb([01])E)?(?:Lb([01])E)?", name)
     if not m:
         return name[:60], None, None
     form, stage, order, nw, xg, mh = m.groups()
     nw = int(nw)
-    rows = {"v5": nw - 2, "v5r": nw - 2, "v3": nw - 2}.get(form)
+    rows = {"v5": nw - 2, "v5r": nw - 2, "v5rb": nw - 2, "v3": nw - 2}.get(form)
     planes = 2
     if form == "v6":
         rows = nw - 1 if mh == "1" else nw - 2
