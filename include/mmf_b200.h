@@ -175,6 +175,12 @@ int mmf_device_count(void); /* number of usable sm_100 devices (0 on a CPU-only 
 /* Replaces: direct rawData() access to cellConservatives / cellConservativesWork / cellRHS.     */
 int mmf_set_state(mmf_ctx *ctx, int field, const double *host_aos);
 int mmf_get_state(mmf_ctx *ctx, int field, double *host_aos);
+/* Replaces: the per-cell utils::conservative2primitive loop main.cpp runs before every mesh.write()
+ * (src/main.cpp:511-518, :531-538; src/utils.cpp:48-63): the primitive fields {p,u,v,w,T}
+ * (src/constants.hpp:37-47) of conservative field `field`, evaluated on the device with IEEE
+ * divisions, AoS in raw cell order like cellPrimitives.rawData(0).  Every cell is converted,
+ * solved or not, as in the reference.                                                            */
+int mmf_get_primitives(mmf_ctx *ctx, int field, double *host_aos);
 
 /* ---- operators with the reference call shape ----------------------------------------------- */
 /* reconstruction::computePolynomials (src/reconstruction.hpp:41-42, reconstruction.cpp:47-55):

@@ -92,6 +92,7 @@ SIGNATURES = {
     "mmf_device_count": (C.c_int, []),
     "mmf_set_state": (C.c_int, [_P, C.c_int, _P]),
     "mmf_get_state": (C.c_int, [_P, C.c_int, _P]),
+    "mmf_get_primitives": (C.c_int, [_P, C.c_int, _P]),
     "mmf_compute_polynomials": (C.c_int, [_P, C.c_int]),
     "mmf_compute_rhs": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "mmf_compute_rhs_host": (C.c_int, [_P, _P, C.c_int, _P, _D]),

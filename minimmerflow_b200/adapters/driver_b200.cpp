@@ -61,9 +61,15 @@ void downloadForOutput(mmf_ctx *ctx, int order, bool haveStep, CellStorageDouble
     if (mmf_get_state(ctx, MMF_FIELD_RHS, rhs->rawData(0)) != MMF_OK) mmf_b200::fail("mmf_get_state", ctx);
 }
 
-// cons -> prim for the writer (what main.cpp does before every mesh.write(), src/main.cpp:511-518)
-void refreshPrimitives(const std::vector<std::size_t> &cellRawIds, const CellStorageDouble &cons, CellStorageDouble *prim)
+// cons -> prim for the writer (what main.cpp does before every mesh.write(), src/main.cpp:511-518): evaluated
+// on the device from the resident state; before the first upload there is nothing resident yet
+void refreshPrimitives(mmf_ctx *ctx, const std::vector<std::size_t> &cellRawIds, const CellStorageDouble &cons,
+                       CellStorageDouble *prim)
 {
+    if (ctx) {
+        if (mmf_get_primitives(ctx, MMF_FIELD_U, prim->rawData(0)) != MMF_OK) mmf_b200::fail("mmf_get_primitives", ctx);
+        return;
+    }
     for (std::size_t raw : cellRawIds) ::utils::conservative2primitive(cons.rawData(raw), prim->rawData(raw));
 }
 
@@ -127,7 +133,7 @@ int main(int argc, char *argv[])
     for (std::size_t raw : cellRawIds) {
         problem::evalCellInitalConservatives(setup.problemType, mesh.getCells().rawAt(raw), meshInfo, cellConservatives.rawData(raw));
     }
-    refreshPrimitives(cellRawIds, cellConservatives, &cellPrimitives);
+    refreshPrimitives(nullptr, cellRawIds, cellConservatives, &cellPrimitives); // nothing is resident yet
     mesh.write();
 
     double minCellSize = std::numeric_limits<double>::max();
@@ -156,13 +162,14 @@ int main(int argc, char *argv[])
         if (t > nextSave) { // output only when due; the state comes back to the host for it
             const auto t0 = std::chrono::steady_clock::now();
             downloadForOutput(ctx, setup.order, true, &cellConservatives, &cellRHS);
-            refreshPrimitives(cellRawIds, cellConservatives, &cellPrimitives);
+            refreshPrimitives(ctx, cellRawIds, cellConservatives, &cellPrimitives);
             mesh.write();
             outputSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             nextSave += (setup.tMax - setup.tMin) / setup.nSaves;
         }
     }
     downloadForOutput(ctx, setup.order, step > 0, &cellConservatives, &cellRHS);
+    refreshPrimitives(ctx, cellRawIds, cellConservatives, &cellPrimitives); // for the final write below
     const double wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wallStart).count();
     mmf_info info;
     mmf_get_info(ctx, &info);
@@ -171,7 +178,6 @@ int main(int argc, char *argv[])
     {
         std::stringstream name;
         name << "final_background_" << setup.cellsPerDirection;
-        refreshPrimitives(cellRawIds, cellConservatives, &cellPrimitives);
         mesh.write(name.str());
     }
     log::cout() << "Computation time (without disk saving time) is " << wallSeconds - outputSeconds << std::endl;

@@ -42,6 +42,28 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(const double *__restric
     for (int i = threadIdx.x; i < n * NF; i += 256) aos[c0 * NF + i] = tile[i];
 }
 
+// utils::conservative2primitive (src/utils.cpp:48-63) over an AoS stream, in place: what main.cpp does for
+// every cell before mesh.write() (src/main.cpp:511-518).  One cell per thread through a shared-memory tile,
+// so that the 40-byte records are read and written as one contiguous stream per block.
+__global__ void __launch_bounds__(256) aos_cons_to_prim_kernel(double *__restrict__ aos, int64_t n_cells)
+{
+    __shared__ double tile[256 * NF];
+    const int64_t c0 = (int64_t) blockIdx.x * 256;
+    const int64_t n  = min((int64_t) 256, n_cells - c0);
+    for (int i = threadIdx.x; i < n * NF; i += 256) tile[i] = aos[c0 * NF + i];
+    __syncthreads();
+    if (threadIdx.x < n) {
+        double c[NF], p[NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) c[k] = tile[threadIdx.x * NF + k];
+        conservative2primitive(c, p);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) tile[threadIdx.x * NF + k] = p[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * NF; i += 256) aos[c0 * NF + i] = tile[i];
+}
+
 // ---- euler::computeRHS (src/euler.cpp:127-249) --------------------------------------------------
 
 __device__ __forceinline__ void load_cell(const double *__restrict__ S, int64_t stride, int64_t c, double *u)

@@ -308,7 +308,7 @@ static int set_state_enqueue(mmf_ctx *ctx, int field, const double *host_aos)
     return MMF_OK;
 }
 
-static int get_state_enqueue(mmf_ctx *ctx, int field, double *host_aos)
+static int get_state_enqueue(mmf_ctx *ctx, int field, double *host_aos, bool primitives = false)
 {
     int rc = ensure_staging(ctx);
     if (rc) return rc;
@@ -318,6 +318,10 @@ static int get_state_enqueue(mmf_ctx *ctx, int field, double *host_aos)
     } else {
         soa_to_aos_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(
             ctx->fields[field], ctx->staging, ctx->n_cells, ctx->gm.stride);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    if (primitives) { // cons -> prim on the staged AoS stream, before it leaves the device
+        aos_cons_to_prim_kernel<<<grid_for(ctx->n_cells, 256), 256, 0, ctx->stream>>>(ctx->staging, ctx->n_cells);
         MMF_LAUNCH_CHECK(ctx);
     }
     const size_t bytes = sizeof(double) * NF * (size_t) ctx->n_cells;
@@ -341,6 +345,17 @@ extern "C" int mmf_get_state(mmf_ctx *ctx, int field, double *host_aos)
     if (rc) return rc;
     if (!host_aos) return fail(ctx, MMF_ERR_INVALID, "mmf_get_state: null buffer");
     if ((rc = get_state_enqueue(ctx, field, host_aos))) return rc;
+    MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMF_OK;
+}
+
+extern "C" int mmf_get_primitives(mmf_ctx *ctx, int field, double *host_aos)
+{
+    int rc = check_field(ctx, field, "mmf_get_primitives");
+    if (rc) return rc;
+    if (!host_aos) return fail(ctx, MMF_ERR_INVALID, "mmf_get_primitives: null buffer");
+    if (field == MMF_FIELD_RHS) return fail(ctx, MMF_ERR_INVALID, "mmf_get_primitives: the residual is not a conservative state");
+    if ((rc = get_state_enqueue(ctx, field, host_aos, true))) return rc;
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMF_OK;
 }

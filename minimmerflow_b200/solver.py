@@ -155,6 +155,14 @@ class EulerSolver:
         self._ck(self._lib.mmf_get_state(self._h, field, out.ctypes.data))
         return out
 
+    def get_primitives(self, field=A.FIELD_U, out=None):
+        """{p,u,v,w,T} per cell: utils::conservative2primitive (src/utils.cpp:48-63) evaluated on the device,
+        what src/main.cpp:511-518 computes for the writer before every mesh.write()."""
+        if out is None:
+            out = np.empty((self.n_cells, A.N_FIELDS), dtype=np.float64)
+        self._ck(self._lib.mmf_get_primitives(self._h, field, out.ctypes.data))
+        return out
+
     def set_state_ptr(self, field, ptr):
         self._ck(self._lib.mmf_set_state(self._h, field, ptr))
 

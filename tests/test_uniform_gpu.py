@@ -95,6 +95,38 @@ def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
         assert bits_equal(s.get_state(mmf.FIELD_W), Wo)
 
 
+@_exp   # entry point added after the round's last GPU call: opt-in like the unmeasured kernel forms
+@pytest.mark.parametrize("generic", [False, True])
+def test_get_primitives_is_conservative2primitive(mmf, oracle, generic):
+    """mmf_get_primitives = the utils::conservative2primitive loop src/main.cpp:511-518 runs before every
+    mesh.write(), evaluated on the device: bitwise the oracle's (src/utils.cpp:48-63), on both paths, for
+    U and for the work field."""
+    import ctypes as C
+    D = C.POINTER(C.c_double)
+    m = oracle.problem_mesh("vortex_xy", 3, 16)
+    rng = np.random.default_rng(5)
+    nc = m["volume"].shape[0]
+    rho = rng.uniform(0.3, 2.0, nc); vel = rng.uniform(-2, 2, (nc, 3)); p = rng.uniform(0.2, 3, nc)
+    U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+    W = oracle.init_state(m)
+
+    def c2p(S):
+        out = np.empty_like(S)
+        for c in range(nc):
+            oracle.lib.orc_conservative2primitive(S[c].ctypes.data_as(D), out[c].ctypes.data_as(D))
+        return out
+
+    with mmf.EulerSolver.from_mesh(m, flags=mmf.FLAG_FORCE_GENERIC if generic else 0) as s:
+        assert s.info()["path"] == (mmf.PATH_GENERIC if generic else mmf.PATH_UNIFORM)
+        s.set_state(mmf.FIELD_U, U)
+        s.set_state(mmf.FIELD_W, W)
+        assert bits_equal(s.get_primitives(mmf.FIELD_U), c2p(U))
+        assert bits_equal(s.get_primitives(mmf.FIELD_W), c2p(W))
+        assert bits_equal(s.get_state(mmf.FIELD_U), U)          # the resident state is untouched
+        with pytest.raises(mmf.MmfError):
+            s.get_primitives(mmf.FIELD_RHS)
+
+
 def _body_meshes(oracle):
     yield "radsod 32^3 + body", oracle.problem_mesh("radsod", 3, 32, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
     yield "sod3d_x 16^3 + bodies at the border", oracle.problem_mesh(

@@ -7,7 +7,7 @@ set -u
 mkdir -p gpurun_out
 export MMF_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp, w = + two y rows per warp, b = box with bodies), bounded
-timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps or bodies" > gpurun_out/experimental_parity.log 2>&1
+timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps or bodies or primitives" > gpurun_out/experimental_parity.log 2>&1
 echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
 tail -5 gpurun_out/experimental_parity.log
 # 2. sweep at the benchmark size: per-stage kernel times, bitwise equality with the default mix
