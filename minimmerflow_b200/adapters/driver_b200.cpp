@@ -12,6 +12,8 @@
 #include "body.hpp"
 #include "memory.hpp"
 #include "solver_writer.hpp"
+
+#include <cstdlib>
 #include "utils.hpp"
 
 #include <bitpit_IO.hpp>
@@ -66,7 +68,9 @@ void downloadForOutput(mmf_ctx *ctx, int order, bool haveStep, CellStorageDouble
 void refreshPrimitives(mmf_ctx *ctx, const std::vector<std::size_t> &cellRawIds, const CellStorageDouble &cons,
                        CellStorageDouble *prim)
 {
-    if (ctx) {
+    // (opt-in until the entry point has run on a GPU: MMF_DEVICE_PRIMITIVES=1; otherwise the reference's host loop)
+    static const bool onDevice = std::getenv("MMF_DEVICE_PRIMITIVES") && std::atoi(std::getenv("MMF_DEVICE_PRIMITIVES"));
+    if (ctx && onDevice) {
         if (mmf_get_primitives(ctx, MMF_FIELD_U, prim->rawData(0)) != MMF_OK) mmf_b200::fail("mmf_get_primitives", ctx);
         return;
     }
