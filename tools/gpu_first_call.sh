@@ -10,6 +10,11 @@ export MMF_TEST_EXPERIMENTAL=1
 timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps or bodies or primitives" > gpurun_out/experimental_parity.log 2>&1
 echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
 tail -5 gpurun_out/experimental_parity.log
+# 1b. the reference's own main on the new pieces: golden strings and bitwise reference fields (bodies included)
+#     with the body cases on the fused path and the writer's primitives from the device
+MMF_UNIFORM_BODIES=1 MMF_DEVICE_PRIMITIVES=1 timeout 600 python -m pytest tests/test_dropin_gpu.py tests/test_reference_fields_gpu.py -m gpu -x -q > gpurun_out/experimental_dropin.log 2>&1
+echo "drop-in exit code: $?" | tee -a gpurun_out/experimental_dropin.log
+tail -3 gpurun_out/experimental_dropin.log
 # 2. sweep at the benchmark size: per-stage kernel times, bitwise equality with the default mix
 timeout 600 python tools/stage_sweep.py --size 256 --steps 6 > gpurun_out/stage_sweep_256.jsonl 2> gpurun_out/stage_sweep_256.err
 cat gpurun_out/stage_sweep_256.jsonl
