@@ -97,10 +97,17 @@ def main():
         os.makedirs(sass_dir, exist_ok=True)
         text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
         chunks = re.split(r"\n(?=\s*Function : )", text)
-        want = {"uniform_stage_kernel_v5ILi0ELi0ELi16": "stage0_rhs_only_v5_16warps",
-                "uniform_stage_kernel_v5ILi1ELi0ELi16": "stage1_v5_16warps",
-                "uniform_stage_kernel_v5rILi2ELi0ELi12": "stage2_v5r_12warps",
-                "uniform_stage_kernel_v5rILi3ELi0ELi12": "stage3_v5r_12warps",
+        # (ELb0 = padded x ghost columns: the single-GPU instantiation the bench runs)
+        want = {"uniform_stage_kernel_v5ILi0ELi0ELi16ELb0": "stage0_rhs_only_v5_16warps",
+                "uniform_stage_kernel_v5ILi1ELi0ELi16ELb0": "stage1_v5_16warps",
+                "uniform_stage_kernel_v5rILi2ELi0ELi12ELb0": "stage2_v5r_12warps",
+                "uniform_stage_kernel_v5rILi3ELi0ELi12ELb0": "stage3_v5r_12warps",
+                # candidates not yet timed on the GPU (opt-in forms d / h / w / b), stage 2
+                "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb0": "candidate_stage2_v6_12warps",
+                "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb1": "candidate_stage2_v6h_12warps",
+                "uniform_stage_kernel_v7ILi2ELi0ELi8ELb0": "candidate_stage2_v7_8warps",
+                "uniform_stage_kernel_v5rbILi2ELi0ELi12": "candidate_stage2_v5rb_bodies_12warps",
+                "uniform_eig_body_kernel": "candidate_uniform_eig_body",
                 "uniform_eig_kernel": "uniform_eig", "uniform_ghost_kernel": "uniform_ghost",
                 "generic_rhs_kernel": "generic_rhs", "generic_rk_kernelILi1": "generic_rk_stage1",
                 "uniform_layer_kernel": "uniform_layer_pack"}
@@ -111,6 +118,7 @@ def main():
             for key, fname in want.items():
                 if key in m.group(1):
                     body = re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/", "", c)
+                    body = body.split("\nFatbin elf code:")[0]
                     body = "\n".join(ln.rstrip() for ln in body.splitlines() if ln.strip())
                     open(os.path.join(sass_dir, fname + ".sass"), "w").write(body + "\n")
 
