@@ -22,6 +22,14 @@
 
 namespace mmf {
 
+// The wall slow path is a call by default: ptxas then spills around three call sites per plane (472 bytes, 48
+// local-memory instructions per plane statically at stage 2).  -DMMF_WALL_INLINE=__forceinline__ (Makefile
+// EXTRA=..., OUT=... for a second library) inlines it instead: 124 bytes of spill, 22 local-memory
+// instructions, but three copies of the path in the plane loop (2090 instead of 814 instructions per plane).
+// Which one is faster is a measurement the first GPU call on this form has to make.
+#ifndef MMF_WALL_INLINE
+#define MMF_WALL_INLINE __noinline__
+#endif
 struct WallFlux {
     double AF[NF];
     double lam;
@@ -39,7 +47,7 @@ __device__ __forceinline__ void wall_side(const double *U, const DivConsts &dc, 
 // conservative state.  fluid_is_low: the fluid cell is the owner, the boundary condition sees the interface
 // normal; otherwise it sees the flipped normal -1.*n (src/euler.cpp:205-224), the splitting the un-flipped
 // one (:232).
-static __device__ __noinline__ WallFlux wall_face(const int axis, const int fluid_is_low, const double u0, const double u1,
+static __device__ MMF_WALL_INLINE WallFlux wall_face(const int axis, const int fluid_is_low, const double u0, const double u1,
                                            const double u2, const double u3, const double u4, const double Ah,
                                            const double y_gm1, const double y_c1)
 {
