@@ -1,5 +1,5 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<p|r|d|t|h|w|b> -DMMF_TU_FORM_ID=<0..6> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<p|r|d|t|h|w|b|c> -DMMF_TU_FORM_ID=<0..7> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 #include "uniform_launch.cuh"
 
@@ -19,10 +19,10 @@
 #include "uniform_stage_v3.cuh"
 #elif MMF_TU_FORM_ID == 5
 #include "uniform_stage_v7.cuh"
-#elif MMF_TU_FORM_ID == 6
+#elif MMF_TU_FORM_ID == 6 || MMF_TU_FORM_ID == 7
 #include "uniform_stage_v5rb.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t), 4 (h), 5 (w) or 6 (b)"
+#error "MMF_TU_FORM_ID must be 0 (p), 1 (r), 2 (d), 3 (t), 4 (h), 5 (w), 6 (b) or 7 (c)"
 #endif
 
 namespace mmf {
@@ -37,7 +37,24 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     return launch_stage_v3(ctx, uniform_stage_kernel_v3<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
 #elif MMF_TU_FORM_ID == 6
     (void) sh;
-    return launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12>, STAGE, Sin, Un, Out, d_max);
+    return launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12, false>, STAGE, Sin, Un, Out, d_max);
+#elif MMF_TU_FORM_ID == 7
+    (void) sh;
+    // wall cells into the compact buffer, the stage kernel (which does not store them), the buffer into the output
+    UniformPath *uw = ctx->uni;
+    if (!uw->wall_list || !uw->wall_compact) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'c' needs the wall-cell list");
+    if (uw->n_wall > 0) {
+        uniform_wall_cells_kernel<STAGE, ORDER><<<(uw->n_wall + 127) / 128, 128, 0, ctx->stream>>>(
+            uw->g, uniform_load_clamp(uw), Sin, Un, uw->solid, uw->wall_list, uw->n_wall, ctx->d_ctl, uw->wall_compact, d_max);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    if (int rc = launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12, true>, STAGE, Sin, Un, Out, d_max)) return rc;
+    if (uw->n_wall > 0) {
+        uniform_wall_scatter_kernel<<<(uw->n_wall + 127) / 128, 128, 0, ctx->stream>>>(uw->g.fs, uw->wall_list, uw->n_wall,
+                                                                                       uw->wall_compact, Out, ctx->d_ctl, STAGE >= 1);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
 #else
     const bool xgk = uniform_use_xghost(ctx);
 #if MMF_TU_FORM_ID == 5

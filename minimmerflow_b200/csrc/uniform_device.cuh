@@ -158,7 +158,7 @@ __device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const doub
                                                 const unsigned char *__restrict__ solid, const int i, const int j, const int k)
 {
     const long long o = uoff(g, i, j, k);
-    if (solid[o]) return 0.0;
+    if (solid[o] == 1) return 0.0; // (2 = a fluid cell next to a wall, kernel form 'c')
     DivConsts dc;
     dc.y_gm1 = rcp_nr(GM1); dc.y_c1 = rcp_nr(TWO_OVER_GM1); dc.y_vol = 0.0;
     double c[NF];
@@ -181,7 +181,7 @@ __device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const doub
 #pragma unroll
             for (int f = 0; f < NF; ++f) v[f] = Sin[f * g.fs + on];
         } else {
-            if (!solid[on]) continue;
+            if (solid[on] != 1) continue;
             // wall: interface normal +e_axis with the low cell as owner; the BC sees it from the fluid side
             double bn[3] = { 0.0, 0.0, 0.0 };
             bn[axis] = 1.0;
@@ -192,6 +192,107 @@ __device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const doub
         derive_cell(v, dc, pv);
         const double lam = fabs(axis == 0 ? pv.u : axis == 1 ? pv.v : pv.w) + pv.a;
         lmax = (lam < lmax) ? lmax : lam;
+    }
+    return lmax;
+}
+
+// ---- a box with bodies, fix-up formulation (kernel form 'c') ------------------------------------------------
+// Flag values: 0 = fluid, 1 = not solved (solid), 2 = fluid cell with at least one wall interface.  The stage
+// kernel proper treats a wall like an ordinary interface (its result for a flag-2 cell is meaningless and is
+// not stored); those cells -- a surface -- are recomputed here, one thread per cell, reference-shaped: the
+// cell's six interfaces in the reference's processing order (src/euler.cpp:153-248; interior low faces by
+// descending creator key, then (-a if border) +a per axis, uniform_stage_v5.cuh), each with
+// euler::evalSplitting's own operations, wall and border sides from euler::evalInterfaceBCValues, then the RK
+// stage of src/main.cpp:409-495.  Returns the largest interface eigenvalue met.
+template <int STAGE, int ORDER>
+__device__ __forceinline__ double wall_cell_update(const UniformGeom &g, const LoadClamp &lc, const double *__restrict__ Sin,
+                                                   const double *__restrict__ Un, const unsigned char *__restrict__ flag,
+                                                   const long long o, const double dt, double *out)
+{
+    const long long plane = (long long) g.py * g.px;
+    const int k = (int) (o / plane) - 1, j = (int) ((o % plane) / g.px) - 1, i = (int) (o % g.px) - 1;
+    const int ijk[3] = { i, j, k }, gijk[3] = { g.gx0 + i, g.gy0 + j, g.gz0 + k }, ext[3] = { g.nx, g.ny, g.nz };
+    const long long step[3] = { 1, g.px, plane };
+    // processing order of the six face slots (0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z)
+    int order[6], n = 0;
+    if (ORDER == NUM_AXIS) {
+        for (int s = 0; s < 6; ++s) order[n++] = s;
+    } else {
+        int lows[3], keys[3], nl = 0;
+        for (int a = 0; a < 3; ++a) {
+            if (gijk[a] == 0) continue;
+            lows[nl] = a;
+            keys[nl] = (ORDER == NUM_LEXI) ? a : 3 * (__ffs(gijk[a]) - 1) + a;
+            nl++;
+        }
+        for (int a = 0; a < nl; ++a)
+            for (int b = a + 1; b < nl; ++b)
+                if (keys[b] > keys[a]) { const int tk = keys[a]; keys[a] = keys[b]; keys[b] = tk; const int tl = lows[a]; lows[a] = lows[b]; lows[b] = tl; }
+        for (int a = 0; a < nl; ++a) order[n++] = 2 * lows[a];
+        for (int a = 0; a < 3; ++a) {
+            if (gijk[a] == 0) order[n++] = 2 * a;
+            order[n++] = 2 * a + 1;
+        }
+    }
+    double c[NF], acc[NF] = { 0., 0., 0., 0., 0. };
+#pragma unroll
+    for (int f = 0; f < NF; ++f) c[f] = Sin[f * g.fs + o];
+    double lmax = 0.0;
+    for (int q = 0; q < 6; ++q) {
+        const int side = order[q], axis = side >> 1;
+        const bool hi = side & 1;
+        const long long on = hi ? o + step[axis] : o - step[axis];
+        const bool border = hi ? (ijk[axis] == ext[axis] - 1) : (ijk[axis] == 0);
+        double nrm[3] = { 0.0, 0.0, 0.0 };
+        double other[NF], flux[NF], lambda;
+        bool cell_is_owner;
+        if (border) {
+            // the cell owns its border interface, outward normal; the ghost cell holds the virtual state, except
+            // on a free-flow side inside a fused step, where it is the copy the stage kernels never read
+            nrm[axis] = hi ? 1.0 : -1.0;
+            cell_is_owner = true;
+            if (g.bc[side] == BC_FREE_FLOW) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) other[f] = c[f];
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) other[f] = Sin[f * g.fs + on];
+            }
+        } else {
+            nrm[0] = 0.0; nrm[axis] = 1.0;          // interior: owner = the low cell, normal +e_axis
+            cell_is_owner = hi;
+            if (flag[on] == 1) {
+                double bn[3] = { nrm[0], nrm[1], nrm[2] };
+                if (!cell_is_owner) { bn[0] = -1. * nrm[0]; bn[1] = -1. * nrm[1]; bn[2] = -1. * nrm[2]; }
+                interface_bc_values(BC_WALL, bn, nullptr, c, other);
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) other[f] = Sin[f * g.fs + on];
+            }
+        }
+        if (cell_is_owner) eval_splitting(c, other, nrm, flux, &lambda);
+        else               eval_splitting(other, c, nrm, flux, &lambda);
+        lmax = (lambda < lmax) ? lmax : lambda;
+        if (cell_is_owner) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] -= g.area * flux[f];
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f] += g.area * flux[f];
+        }
+    }
+    (void) lc;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        if (STAGE == 0) {
+            out[f] = acc[f];
+        } else {
+            const double qd = dt * acc[f] / g.volume;
+            const double un = (STAGE >= 2) ? Un[f * g.fs + o] : 0.0;
+            if (STAGE == 1)      out[f] = c[f] + qd;
+            else if (STAGE == 2) out[f] = 0.75 * un + 0.25 * (c[f] + qd);
+            else                 out[f] = (1. / 3) * un + (2. / 3) * (c[f] + qd);
+        }
     }
     return lmax;
 }

@@ -21,7 +21,8 @@ namespace mmf {
 //       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 warps; opt-in likewise), '3' the older
 //       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check, 'b' the rotate
 //       form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never by
-//       MMF_STAGE_CFG)
+//       MMF_STAGE_CFG), 'c' the same with the wall cells recomputed by a small pass around the stage kernel
+//       instead of a slow path inside it
 struct StageShape {
     char form = 'p';
     int nw = 16;
@@ -51,6 +52,12 @@ struct UniformPath {
     // the ghost shell repeats the flag of the cell it touches
     unsigned char *solid = nullptr;
     bool bodies = false;              // set before the arrays are laid out: selects kernel form 'b' for every stage
+    // MMF_UNIFORM_BODIES=2: form 'c' instead -- flag 2 marks the fluid cells with a wall interface, which the stage
+    // kernel does not store and wall_cell_update recomputes (list of their padded offsets, compact result buffer)
+    bool bodies_fixup = false;
+    int *wall_list = nullptr;
+    int n_wall = 0;
+    double *wall_compact = nullptr;
     int nbr_rank[6] = { -1, -1, -1, -1, -1, -1 };
     double *send_buf[6] = {}, *recv_buf[6] = {};
     // direct peer stores over NVLink (comm.cuh): the neighbours' state arrays and arrival flags,
@@ -224,12 +231,13 @@ MMF_DECLARE_STAGE_TUS(h)  // uniform_stage_v6.cuh, one warp for both halo rows
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_v3.cuh (form '3')
 MMF_DECLARE_STAGE_TUS(w)  // uniform_stage_v7.cuh, two y rows per warp
 MMF_DECLARE_STAGE_TUS(b)  // uniform_stage_v5rb.cuh, a box with bodies
+MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies, wall cells by a fix-up pass
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3', 'b') for a stage
+// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3', 'b', 'c') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[7][4] = {
+    static const StageLauncher tab[8][4] = {
         { launch_stage_p_0, launch_stage_p_1, launch_stage_p_2, launch_stage_p_3 },
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
         { launch_stage_d_0, launch_stage_d_1, launch_stage_d_2, launch_stage_d_3 },
@@ -237,8 +245,9 @@ inline StageLauncher stage_launcher(char form, int stage)
         { launch_stage_h_0, launch_stage_h_1, launch_stage_h_2, launch_stage_h_3 },
         { launch_stage_w_0, launch_stage_w_1, launch_stage_w_2, launch_stage_w_3 },
         { launch_stage_b_0, launch_stage_b_1, launch_stage_b_2, launch_stage_b_3 },
+        { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
     };
-    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : (form == 'b') ? 6 : 0;
+    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : (form == 'b') ? 6 : (form == 'c') ? 7 : 0;
     return tab[f][stage];
 }
 

@@ -143,7 +143,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         }
     }
     if (u->bodies) { // a box with bodies: the one kernel form that knows about them, whatever MMF_STAGE_CFG says
-        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'b', 12 };
+        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ u->bodies_fixup ? 'c' : 'b', 12 };
     }
     // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
     // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
@@ -371,6 +371,7 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
     u->iface_numbering = numbering;
     u->order_exact = order_exact;
     u->bodies = bodies;
+    u->bodies_fixup = bodies && atoi(getenv("MMF_UNIFORM_BODIES")) == 2;
     ctx->path = MMF_PATH_UNIFORM;
     int rc = uniform_alloc(ctx, u);
     if (rc) return rc;
@@ -396,6 +397,31 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
                 flag[(size_t) uoff(g, i, j, -1)] = flag[(size_t) uoff(g, i, j, 0)];
                 flag[(size_t) uoff(g, i, j, nz)] = flag[(size_t) uoff(g, i, j, nz - 1)];
             }
+        if (u->bodies_fixup) {
+            // fluid cells with a wall interface: flag 2, listed by padded offset (ascending: coalesced enough)
+            std::vector<int> walls;
+            const long long step[3] = { 1, g.px, (long long) g.py * g.px };
+            for (int k = 0; k < nz; ++k)
+                for (int j = 0; j < ny; ++j)
+                    for (int i = 0; i < nx; ++i) {
+                        const long long o = uoff(g, i, j, k);
+                        if (flag[(size_t) o] == 1) continue;
+                        const int ijk[3] = { i, j, k }, ext[3] = { nx, ny, nz };
+                        bool wall = false;
+                        for (int a = 0; a < 3; ++a) {
+                            if (ijk[a] > 0 && flag[(size_t) (o - step[a])] == 1) wall = true;
+                            if (ijk[a] < ext[a] - 1 && flag[(size_t) (o + step[a])] == 1) wall = true;
+                        }
+                        if (wall) walls.push_back((int) o);
+                    }
+            for (int o : walls) flag[(size_t) o] = 2;
+            // (the ghost shell was filled before: it repeats 0 / 1 of the cell it touches; a flag-2 border cell's
+            //  ghost stays 0, which is what the stage kernel's border interface needs)
+            u->n_wall = (int) walls.size();
+            if (walls.empty()) walls.push_back(0);
+            if ((rc = dev_upload(ctx, &u->wall_list, walls))) return rc;
+            if ((rc = dev_alloc(ctx, &u->wall_compact, (size_t) NF * walls.size()))) return rc;
+        }
         if ((rc = dev_upload(ctx, &u->solid, flag))) return rc;
     }
     std::vector<int> off((size_t) nc);

@@ -69,14 +69,17 @@ static __device__ MMF_WALL_INLINE WallFlux wall_face(const int axis, const int f
     return r;
 }
 
-// the interface (low | high) along AXIS; a negative lam marks a solid side
-template <int AXIS>
+// the interface (low | high) along AXIS; a negative lam marks a solid side.  FIXUP (kernel form 'c'): a wall is
+// evaluated like any interface here -- the fluid cell it belongs to is not stored by this kernel but recomputed
+// by wall_cell_update (uniform_device.cuh) -- so the hot path has no call and no divergent branch; the value of
+// max(lam_fluid, -1) = lam_fluid it contributes to the face maximum is one the true maximum contains anyway.
+template <int AXIS, bool FIXUP>
 __device__ __forceinline__ double body_face_flux(const double *LU, const double *LF, const double ll, const double *HU,
                                                  const double *HF, const double hl, const double Ah, const DivConsts &dc,
                                                  double *AF)
 {
     const bool sl = ll < 0.0, sh = hl < 0.0;
-    if (sl == sh) return llf_area_flux(LU, LF, ll, HU, HF, hl, Ah, AF);
+    if (FIXUP || sl == sh) return llf_area_flux(LU, LF, ll, HU, HF, hl, Ah, AF);
     const WallFlux w = wall_face(AXIS, sh ? 1 : 0, sh ? LU[0] : HU[0], sh ? LU[1] : HU[1], sh ? LU[2] : HU[2],
                                  sh ? LU[3] : HU[3], sh ? LU[4] : HU[4], Ah, dc.y_gm1, dc.y_c1);
 #pragma unroll
@@ -84,7 +87,7 @@ __device__ __forceinline__ double body_face_flux(const double *LU, const double 
     return w.lam;
 }
 
-template <int STAGE, int ORDER, int NW>
+template <int STAGE, int ORDER, int NW, bool FIXUP>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
                           const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
@@ -159,7 +162,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             derive_cell(cU, dc, q);
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
-            if (csol) cly = -1.0;
+            if (csol == 1) cly = -1.0;
             if (it > 0) mbar_wait(&barF[1], (unsigned) ((it - 1) & 1)); // row 1 is done with the previous record
 #pragma unroll
             for (int k = 0; k < NF; ++k) { d[k * 32] = cU[k]; d[(NF + k) * 32] = cFy[k]; }
@@ -195,13 +198,13 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             derive_cell(cU, dc, q);
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
-            if (csol) cly = -1.0;
+            if (csol == 1) cly = -1.0;
             mbar_wait(&barD[NW - 2], (unsigned) (it & 1));
             double lU[NF], lF[NF], AFy[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
             const double ll  = d_dn[10 * 32];
-            const double lam = body_face_flux<1>(lU, lF, ll, cU, cFy, cly, Ah, dc, AFy);
+            const double lam = body_face_flux<1, FIXUP>(lU, lF, ll, cU, cFy, cly, Ah, dc, AFy);
             lmy = (lam < lmy) ? lmy : lam;
             // row NW-2 published record `it` only after it had read flux `it-1`: the slot is free
 #pragma unroll
@@ -232,7 +235,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
         double *op = Out + col + (long long) z0 * plane;        // plane z0-1 (first store goes to plane z0)
 
         double pU[NF], pFz[NF], plz, pS[NF], pUn[NF], nxt[NF];
-        unsigned nsol;
+        unsigned nsol, pflag; // pflag: flag of the previous plane's cell (a cell is stored only if it is 0)
         double lmx = 0.0, lmy = 0.0, lmz = 0.0;
         // ---- prologue: plane z0-1 only provides the low side of the first z interface --------------
         {
@@ -247,7 +250,8 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             CellPrim q;
             derive_cell(pU, dc, q);
             axis_flux<2>(q, pFz, plz);
-            if (psol) plz = -1.0;
+            if (psol == 1) plz = -1.0;
+            pflag = psol;
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pS[k] = 0.0; pUn[k] = 0.0; }
         }
@@ -276,7 +280,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             // ---- y record for row+1 (the earlier it is out, the less row+1 waits) ---------------------
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
-            if (csol) cly = -1.0;
+            if (csol == 1) cly = -1.0;
 #pragma unroll
             for (int k = 0; k < NF; ++k) { d_own[k * 32] = cU[k]; d_own[(NF + k) * 32] = cFy[k]; }
             d_own[10 * 32] = cly;
@@ -285,12 +289,12 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             // ---- z interface (kz-1 | kz): completes plane kz-1 (never stored if that cell is solid) ----
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
-            if (csol) clz = -1.0;
+            if (csol == 1) clz = -1.0;
             {
-                const double lam = body_face_flux<2>(pU, pFz, plz, cU, cFz, clz, Ah, dc, AFz);
+                const double lam = body_face_flux<2, FIXUP>(pU, pFz, plz, cU, cFz, clz, Ah, dc, AFz);
                 lmz = (lam < lmz) ? lmz : lam;
             }
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0 && !(plz < 0.0), est_max);
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0 && pflag == 0, est_max);
             op += plane;
 
             // ---- x interface (i-1 | i): lane-1's state by warp shuffle ---------------------------------
@@ -298,11 +302,11 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             {
                 double cFx[NF], clx, lU[NF], lF[NF];
                 axis_flux<0>(q, cFx, clx);
-                if (csol) clx = -1.0;
+                if (csol == 1) clx = -1.0;
 #pragma unroll
                 for (int k = 0; k < NF; ++k) { lU[k] = shfl_up_d(cU[k]); lF[k] = shfl_up_d(cFx[k]); }
                 const double ll  = shfl_up_d(clx);
-                const double lam = body_face_flux<0>(lU, lF, ll, cU, cFx, clx, Ah, dc, AFx);
+                const double lam = body_face_flux<0, FIXUP>(lU, lF, ll, cU, cFx, clx, Ah, dc, AFx);
                 lmx = (lam < lmx) ? lmx : lam;
             }
 
@@ -314,7 +318,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
 #pragma unroll
                 for (int k = 0; k < NF; ++k) { lU[k] = d_dn[k * 32]; lF[k] = d_dn[(NF + k) * 32]; }
                 const double ll  = d_dn[10 * 32];
-                const double lam = body_face_flux<1>(lU, lF, ll, cU, cFy, cly, Ah, dc, AFy);
+                const double lam = body_face_flux<1, FIXUP>(lU, lF, ll, cU, cFy, cly, Ah, dc, AFy);
                 lmy = (lam < lmy) ? lmy : lam;
                 // row-1 published record `it` only after it had read this row's flux `it-1`
 #pragma unroll
@@ -376,6 +380,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pS[k] = S[k]; pU[k] = cU[k]; pFz[k] = cFz[k]; }
             plz = clz;
+            pflag = csol;
             if (STAGE >= 2) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pUn[k] = cUn[k];
@@ -388,10 +393,10 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
             derive_cell(nxt, dc, q);
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
-            if (nsol) clz = -1.0;
-            const double lam = body_face_flux<2>(pU, pFz, plz, nxt, cFz, clz, Ah, dc, AFz);
+            if (nsol == 1) clz = -1.0;
+            const double lam = body_face_flux<2, FIXUP>(pU, pFz, plz, nxt, cFz, clz, Ah, dc, AFz);
             lmz = (lam < lmz) ? lmz : lam;
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && !(plz < 0.0), est_max);
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && pflag == 0, est_max);
         }
         lmax = xf_ok ? lmx : 0.0;
         if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;
@@ -400,6 +405,42 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
     }
 
     block_maxima<NW>(lmax, max_eig, emax, (STAGE == 3) ? cta_est : nullptr, tid.tile, smem);
+}
+
+// the two small kernels around the stage kernel of form 'c': the wall cells' results into a compact buffer
+// BEFORE the stage kernel runs (stage 3 updates U in place: U^n of a wall cell must still be there), and from
+// the buffer into the output array behind it
+template <int STAGE, int ORDER>
+__global__ void __launch_bounds__(128) uniform_wall_cells_kernel(const UniformGeom g, const LoadClamp lc,
+                                                                 const double *__restrict__ Sin, const double *__restrict__ Un,
+                                                                 const unsigned char *__restrict__ flag,
+                                                                 const int *__restrict__ list, const int n_list,
+                                                                 const StepControl *__restrict__ ctl,
+                                                                 double *__restrict__ compact, double *__restrict__ max_eig)
+{
+    if (STAGE >= 1 && ctl->active == 0.0) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    double lmax = 0.0;
+    if (q < n_list) {
+        double out[NF];
+        lmax = wall_cell_update<STAGE, ORDER>(g, lc, Sin, Un, flag, (long long) list[q], (STAGE >= 1) ? ctl->dt : 0.0, out);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) compact[(size_t) f * n_list + q] = out[f];
+    }
+    block_max_to_global(lmax, max_eig);
+}
+
+static __global__ void __launch_bounds__(128) uniform_wall_scatter_kernel(const long long fs, const int *__restrict__ list,
+                                                                   const int n_list, const double *__restrict__ compact,
+                                                                   double *__restrict__ Out,
+                                                                   const StepControl *__restrict__ ctl, const int check_active)
+{
+    if (check_active && ctl->active == 0.0) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_list) return;
+    const long long o = list[q];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) Out[f * fs + o] = compact[(size_t) f * n_list + q];
 }
 
 } // namespace mmf

@@ -96,33 +96,36 @@ def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
     assert np.array_equal(box.gather(R), ref)
 
 
+@pytest.mark.parametrize("form", ["b", "c"])
 @pytest.mark.parametrize("chaos", [0, 300])
-def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, chaos):
-    """Kernel form 'b' (uniform_stage_v5rb.cuh): a uniform box with bodies -- unsolved cells, wall interfaces
+def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, chaos, form):
+    """Kernel forms 'b' and 'c' (uniform_stage_v5rb.cuh; 'c' = wall cells recomputed by wall_cell_update around a
+    stage kernel without a slow path): a uniform box with bodies -- unsolved cells, wall interfaces
     evaluated against the fluid cell's mirror image, solid | solid interfaces skipped -- and the eigenvalue
     pass that chooses dt there (eig_body_cell), bit for bit against the oracle."""
     # the reference's set-up: Morton cube, reflecting borders, a box body inside
     m = oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
     assert (m["solved"] == 0).sum() > 50 and (m["bc"] == 2).sum() > 100
-    assert run_emu.check_case(emu, oracle, "radsod 16^3 + body", dict(m), 0, "b", 12, 6, 2, chaos, 1)
+    assert run_emu.check_case(emu, oracle, "radsod 16^3 + body", dict(m), 0, form, 12, 6, 2, chaos, 1)
     # ragged lexicographic box, free-flow borders (clamped loads), bodies touching the border, a one-cell
     # body and a one-cell gap between two bodies; two-plane z chunks
     m = with_bodies(lexicographic_box_mesh(33, 9, 5, 0.5, 0), [[-1, -1, -1, 1.2, 1.2, 1.2], [7.1, 2.1, 1.1, 7.4, 2.4, 1.4],
                                                                [10.1, 0.0, 0.0, 11.9, 9.0, 1.4], [12.6, 0.0, 0.0, 16.4, 2.4, 9.0]])
     m["problem"] = "vortex_xy"
     assert (m["solved"] == 0).sum() > 30
-    assert run_emu.check_case(emu, oracle, "box 33x9x5 + bodies", dict(m), 1, "b", 12, 2, 2, chaos, 2)
+    assert run_emu.check_case(emu, oracle, "box 33x9x5 + bodies", dict(m), 1, form, 12, 2, 2, chaos, 2)
     # reflecting borders with a body on them
     m = with_bodies(lexicographic_box_mesh(7, 23, 4, 0.5, 1), [[-1, 4.1, -1, 1.4, 6.4, 9.0], [2.1, 10.1, 0.6, 2.9, 11.4, 1.4]])
     m["problem"] = "radsod"
-    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, "b", 8, 3, 2, chaos, 3)
+    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, form, 8, 3, 2, chaos, 3)
 
 
 BODY_CASES_3D = [c for c in reference_cases() if c["dim"] == 3 and c.get("bodies")]
 
 
+@pytest.mark.parametrize("form", ["b", "c"])
 @pytest.mark.parametrize("case", BODY_CASES_3D, ids=lambda c: c["name"])
-def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case):
+def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case, form):
     """The whole run of a reference case with bodies -- dt from the eigenvalue pass (eig_body_cell), three fused
     stages of kernel form 'b' per step, `while (t < tMax)` with the clamp -- driven from the emulator alone and
     compared with the final fields the UNMODIFIED reference wrote (tests/golden/reference_fields.npz)."""
@@ -138,12 +141,12 @@ def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu,
     while t < case["t_end"]:
         eig = box.eig_body(U)
         dt = oracle.choose_dt(case["cfl"], h, eig, t, case["t_end"])
-        e1, _ = box.stage("b", 1, 12, 6, U, U, Wa, dt)
+        e1, _ = box.stage(form, 1, 12, 6, U, U, Wa, dt)
         assert e1 == eig                      # the check mmf_step makes every step
         box.fill_ghosts(Wa)
-        box.stage("b", 2, 12, 6, Wa, U, Wb, dt)
+        box.stage(form, 2, 12, 6, Wa, U, Wb, dt)
         box.fill_ghosts(Wb)
-        box.stage("b", 3, 12, 6, Wb, U, U, dt)
+        box.stage(form, 3, 12, 6, Wb, U, U, dt)
         box.fill_ghosts(U)
         t += dt
         steps += 1

@@ -145,11 +145,12 @@ def test_box_with_bodies_stays_on_the_generic_path_by_default(mmf, oracle, monke
 
 
 @_exp
-def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
-    """Kernel form 'b' (uniform_stage_v5rb.cuh, opt-in MMF_UNIFORM_BODIES=1; checked on the CPU emulator only so
-    far): a uniform box with bodies on the fused path -- RHS, the dt eigenvalue, ten fused steps and the unfused
-    operator sequence, bitwise against the oracle; cells that are not solved keep the host's values."""
-    monkeypatch.setenv("MMF_UNIFORM_BODIES", "1")
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch, mode):
+    """Kernel forms 'b' / 'c' (uniform_stage_v5rb.cuh, opt-in MMF_UNIFORM_BODIES=1 / 2; checked on the CPU emulator
+    only so far): a uniform box with bodies on the fused path -- RHS, the dt eigenvalue, ten fused steps and the
+    unfused operator sequence, bitwise against the oracle; cells that are not solved keep the host's values."""
+    monkeypatch.setenv("MMF_UNIFORM_BODIES", mode)
     rng = np.random.default_rng(11)
     for name, m in _body_meshes(oracle):
         nc = m["volume"].shape[0]

@@ -212,7 +212,8 @@ std::function<void()> bind_kernel(int form, const Args &a)
     case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
+    case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
+    case 'c': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
 #endif
     default: return nullptr;
     }
@@ -240,6 +241,25 @@ std::function<void()> bind_order(int order, int form, int nw, const Args &a)
     }
 }
 
+} // namespace
+
+namespace {
+template <int STAGE>
+double wall_cells_order(int order, const UniformGeom &g, const LoadClamp &lc, const double *Sin, const double *Un,
+                        const unsigned char *flag, const int *list, int n_list, double dt, double *compact)
+{
+    double m = 0.0;
+    for (int q = 0; q < n_list; ++q) {
+        double out[NF];
+        double l;
+        if (order == NUM_MORTON)    l = wall_cell_update<STAGE, NUM_MORTON>(g, lc, Sin, Un, flag, list[q], dt, out);
+        else if (order == NUM_LEXI) l = wall_cell_update<STAGE, NUM_LEXI>(g, lc, Sin, Un, flag, list[q], dt, out);
+        else                        l = wall_cell_update<STAGE, NUM_AXIS>(g, lc, Sin, Un, flag, list[q], dt, out);
+        for (int f = 0; f < NF; ++f) compact[(size_t) f * n_list + q] = out[f];
+        m = (l < m) ? m : l;
+    }
+    return m;
+}
 } // namespace
 
 static mmf::XGhost g_xghost{};
@@ -333,6 +353,30 @@ double emu_eig_body(const int dims[3], const int bc[6], const double *Sin, const
                 m = (l < m) ? m : l;
             }
     return m;
+}
+
+// kernel form 'c': the wall cells of a box with bodies (wall_cell_update, the per-thread body of
+// uniform_wall_cells_kernel) into the compact buffer [field][n_list]; returns the largest interface eigenvalue
+
+double emu_wall_cells(int stage, int order, const int dims[3], const int bc[6], double area, double volume, const int clamp[6],
+                      const double *Sin, const double *Un, const unsigned char *flag, const int *list, int n_list, double dt,
+                      double *compact)
+{
+    UniformGeom g{};
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    g.gnx = dims[0]; g.gny = dims[1]; g.gnz = dims[2];
+    int pad[3];
+    emu_padded(dims, pad, &g.fs);
+    g.px = pad[0]; g.py = pad[1]; g.pz = pad[2];
+    g.area = area; g.volume = volume;
+    for (int s = 0; s < 6; ++s) g.bc[s] = bc[s];
+    const LoadClamp lc = { clamp[0], clamp[1], clamp[2], clamp[3], clamp[4], clamp[5] };
+    switch (stage) {
+    case 0: return wall_cells_order<0>(order, g, lc, Sin, Un, flag, list, n_list, dt, compact);
+    case 1: return wall_cells_order<1>(order, g, lc, Sin, Un, flag, list, n_list, dt, compact);
+    case 2: return wall_cells_order<2>(order, g, lc, Sin, Un, flag, list, n_list, dt, compact);
+    default: return wall_cells_order<3>(order, g, lc, Sin, Un, flag, list, n_list, dt, compact);
+    }
 }
 
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }

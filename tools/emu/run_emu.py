@@ -55,6 +55,9 @@ def load():
     lib.emu_set_spin_limit.argtypes = [C.c_longlong]
     lib.emu_set_xghost.argtypes = [_D, _D, C.c_longlong, C.c_int]
     lib.emu_set_solid.argtypes = [C.c_void_p]
+    lib.emu_wall_cells.restype = C.c_double
+    lib.emu_wall_cells.argtypes = [C.c_int, C.c_int, _I, _I, C.c_double, C.c_double, _I, _D, _D, C.c_void_p, _I, C.c_int,
+                                   C.c_double, _D]
     lib.emu_eig_body.restype = C.c_double
     lib.emu_eig_body.argtypes = [_I, _I, _D, C.c_void_p]
     return lib
@@ -105,6 +108,21 @@ class Box:
             vol[:, :, 0] = vol[:, :, 1]; vol[:, :, nx + 1] = vol[:, :, nx]
             self.solid = np.zeros(self.fs, np.uint8)
             self.solid[:px * py * pz] = vol.reshape(-1)
+            # kernel form 'c': fluid cells with a wall interface get flag 2 and are listed by padded offset
+            # (what uniform_try_create builds with MMF_UNIFORM_BODIES=2)
+            step = (1, px, px * py)
+            walls = []
+            for o, (i, j, k) in sorted(zip(self.off.tolist(), self.ijk.tolist())):
+                if self.solid[o] == 1:
+                    continue
+                ext = (nx, ny, nz)
+                c = (i, j, k)
+                if any((c[a] > 0 and self.solid[o - step[a]] == 1) or (c[a] < ext[a] - 1 and self.solid[o + step[a]] == 1)
+                       for a in range(3)):
+                    walls.append(o)
+            self.flag_c = self.solid.copy()
+            self.flag_c[walls] = 2
+            self.walls = ia(walls)
 
     def new_array(self):
         a = np.empty((5, self.fs))
@@ -187,9 +205,17 @@ class Box:
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
         dirichlet = np.zeros(5)
-        if (self.solid is not None) != (form == "b"):
-            raise RuntimeError("kernel form 'b' is the one for a box with bodies, and only that")
-        self.lib.emu_set_solid(self.solid.ctypes.data if self.solid is not None else None)
+        if (self.solid is not None) != (form in ("b", "c")):
+            raise RuntimeError("kernel forms 'b' and 'c' are the ones for a box with bodies, and only those")
+        flags = self.flag_c if form == "c" else self.solid
+        self.lib.emu_set_solid(flags.ctypes.data if flags is not None else None)
+        e_wall, compact = 0.0, None
+        if form == "c":   # the wall cells BEFORE the stage kernel (stage 3 updates U in place)
+            compact = np.empty((5, max(len(self.walls), 1)))
+            e_wall = self.lib.emu_wall_cells(stage, self.order, self.dims.ctypes.data_as(_I), ia(self.bc).ctypes.data_as(_I),
+                                             float(m["area"][0]), float(m["volume"][0]), self.clamp.ctypes.data_as(_I),
+                                             Sin.ctypes.data_as(_D), Un.ctypes.data_as(_D), flags.ctypes.data,
+                                             self.walls.ctypes.data_as(_I), len(self.walls), dt, compact.ctypes.data_as(_D))
         rc = self.lib.emu_stage(ord(form), stage, self.order, nw, lz, self.dims.ctypes.data_as(_I), zero3.ctypes.data_as(_I),
                                 self.dims.ctypes.data_as(_I), ia(self.bc).ctypes.data_as(_I), float(m["h"]),
                                 float(m["area"][0]), float(m["volume"][0]), dirichlet.ctypes.data_as(_D),
@@ -198,7 +224,9 @@ class Box:
                                 self.smem_doubles(form, nw), chaos, seed)
         if rc:
             raise RuntimeError(f"emu_stage: configuration not built (rc={rc})")
-        return float(me[0]), est
+        if form == "c" and len(self.walls):   # uniform_wall_scatter_kernel
+            Out[:, self.walls] = compact
+        return max(float(me[0]), e_wall), est
 
 
 def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
@@ -259,6 +287,8 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
         want = np.zeros(est.shape[0])
         if box.solid is not None:
             lam = np.where(m["solved"] != 0, lam, 0.0)   # solid cells are never written: no estimate
+            if form == "c":                              # ... nor are the wall cells, by the stage kernel itself
+                lam = np.where(box.flag_c[box.off] == 0, lam, 0.0)
         np.maximum.at(want, tile, lam)
         if not np.allclose(est, want, rtol=2e-5, atol=0):
             ok = False
@@ -270,7 +300,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="p,r,d,h,w,b")
+    ap.add_argument("--forms", default="p,r,d,h,w,b,c")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -281,7 +311,7 @@ def main():
     oracle = oracle_lib.load()
     forms = [f for f in args.forms.split(",") if f]
     if not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        forms = [f for f in forms if f not in ("d", "h", "w", "b")]
+        forms = [f for f in forms if f not in ("d", "h", "w", "b", "c")]
     cases = []
     m = oracle.problem_mesh("vortex_xy", 3, 16)
     cases.append(("vortex 16^3 morton", m, 0, 6))
@@ -294,8 +324,9 @@ def main():
     # boxes with bodies (kernel form 'b' only): a box body off the Morton cube's centre, two bodies touching
     # the border, a one-cell body
     body_cases = []
-    if "b" in forms:
-        forms = [f for f in forms if f != "b"]
+    body_forms = [f for f in forms if f in ("b", "c")]
+    if body_forms:
+        forms = [f for f in forms if f not in ("b", "c")]
         body_cases.append(("radsod 16^3 + box body", oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]]), 0, 6))
         if not args.quick:
             body_cases.append(("sod3d_x 16^3 + 2 bodies at the border", oracle.problem_mesh(
@@ -305,8 +336,9 @@ def main():
     all_ok = True
     for rep in range(args.repeat):
         for name, mesh, order, lz in body_cases:
-            for nw in (int(x) for x in args.nw.split(",")):
-                all_ok &= check_case(lib, oracle, name, dict(mesh), order, "b", nw, lz, args.steps, args.chaos, 1 + 100 * rep)
+            for form in body_forms:
+                for nw in (int(x) for x in args.nw.split(",")):
+                    all_ok &= check_case(lib, oracle, name, dict(mesh), order, form, nw, lz, args.steps, args.chaos, 1 + 100 * rep)
         for name, mesh, order, lz in cases:
             for form in forms:
                 for nw in (int(x) for x in args.nw.split(",")):

@@ -31,7 +31,7 @@ def main():
     orc = oracle_lib.load()
     boxes = None
     if args.bodies:
-        os.environ["MMF_UNIFORM_BODIES"] = "1"
+        os.environ.setdefault("MMF_UNIFORM_BODIES", "1")   # 1 = form b, 2 = form c
         _, origin, length = orc.domain(args.problem, 3)
         lo = lambda f: [origin[e] + f[e] * length for e in range(3)]
         boxes = [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))]
@@ -48,7 +48,7 @@ def main():
             s.run(0.45, m["h"], 0.0, 1e30, max_steps=args.steps)
             ms = s.timer_stop()
             out[name] = s.get_state(mmf.FIELD_U)
-            print(json.dumps({"path": name, "path_code": path, "cells": cells, "solved_cells": int(m["solved"].sum()),
+            print(json.dumps({"path": name, "path_code": path, "bodies_mode": os.environ.get("MMF_UNIFORM_BODIES", "") if args.bodies else "", "cells": cells, "solved_cells": int(m["solved"].sum()),
                               "ms_per_step": ms / args.steps,
                               "cell_updates_per_s": int(m["solved"].sum()) * 3 * args.steps / (ms * 1e-3)}), flush=True)
     print(json.dumps({"bitwise_equal": bool(np.array_equal(out["uniform"], out["generic"]))}))

@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 export MMF_TEST_EXPERIMENTAL=1
-# 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp, w = + two y rows per warp, b = box with bodies), bounded
+# 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp, w = + two y rows per warp, b / c = box with bodies), bounded
 timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps or bodies or primitives" > gpurun_out/experimental_parity.log 2>&1
 echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
 tail -5 gpurun_out/experimental_parity.log
@@ -25,4 +25,7 @@ done
 cat gpurun_out/stage_sweep_lz.jsonl
 timeout 600 python tools/generic_bench.py --size 128 --steps 6 > gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err; cat gpurun_out/generic_bench_128.jsonl
 # 4. a box with bodies: fused uniform path (form b, MMF_UNIFORM_BODIES=1) against the generic path
-timeout 600 python tools/generic_bench.py --size 128 --steps 6 --bodies > gpurun_out/body_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err; cat gpurun_out/body_bench_128.jsonl
+for mode in 1 2; do
+  MMF_UNIFORM_BODIES=$mode timeout 600 python tools/generic_bench.py --size 128 --steps 6 --bodies >> gpurun_out/body_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err
+done
+cat gpurun_out/body_bench_128.jsonl

@@ -106,7 +106,9 @@ def main():
                 "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb0": "candidate_stage2_v6_12warps",
                 "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb1": "candidate_stage2_v6h_12warps",
                 "uniform_stage_kernel_v7ILi2ELi0ELi8ELb0": "candidate_stage2_v7_8warps",
-                "uniform_stage_kernel_v5rbILi2ELi0ELi12": "candidate_stage2_v5rb_bodies_12warps",
+                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb0": "candidate_stage2_v5rb_bodies_12warps",
+                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb1": "candidate_stage2_v5rb_bodies_fixup_12warps",
+                "uniform_wall_cells_kernelILi2ELi0": "candidate_stage2_wall_cells",
                 "uniform_eig_body_kernel": "candidate_uniform_eig_body",
                 "uniform_eig_kernel": "uniform_eig", "uniform_ghost_kernel": "uniform_ghost",
                 "generic_rhs_kernel": "generic_rhs", "generic_rk_kernelILi1": "generic_rk_stage1",

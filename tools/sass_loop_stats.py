@@ -90,6 +90,8 @@ def describe(name):
         form = "v6h" if mh == "1" else "v6"
     if form == "v7":
         rows = 2 * (nw - 1)
+    if form == "v5rb":   # the bool is FIXUP (form 'c'), not the compact x ghosts
+        form, xg = ("v5rc" if xg == "1" else "v5rb"), "0"
     if form == "v3":
         planes = 1
     return "%-4s stage %s order %s nw %2d%s" % (form, stage, order, nw, " xg" if xg == "1" else ""), rows, planes
@@ -98,7 +100,7 @@ def describe(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=LIB)
-    ap.add_argument("--match", default=r"uniform_stage_kernel_v(5|5r|6|7)ILi[0-3]ELi0ELi(8|12|16)ELb0")
+    ap.add_argument("--match", default=r"uniform_stage_kernel_v(5|5r|6|7)ILi[0-3]ELi0ELi(8|12|16)ELb0|uniform_stage_kernel_v5rbILi[0-3]ELi0ELi12")
     ap.add_argument("--rows", type=int, default=0, help="override the rows a CTA updates")
     ap.add_argument("--planes", type=int, default=0, help="override planes per loop trip")
     args = ap.parse_args()
