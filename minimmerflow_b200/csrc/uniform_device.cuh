@@ -7,6 +7,8 @@
 #include "generic_types.cuh"
 #include "ptx_helpers.cuh"
 
+#include <vector>
+
 namespace mmf {
 
 enum { NUM_MORTON = 0, NUM_LEXI = 1, NUM_AXIS = 2 };
@@ -295,6 +297,54 @@ __device__ __forceinline__ double wall_cell_update(const UniformGeom &g, const L
         }
     }
     return lmax;
+}
+
+// ---- a box with bodies: the flag array and the wall-cell list, host side --------------------------------------
+// One flag per padded cell (layout of one field): 1 = not solved (src/main.cpp:221-237).  The ghost shell repeats
+// the flag of the cell it touches, so that the border interface of an unsolved cell is skipped like the
+// reference skips it (src/euler.cpp:181-183).  mark_walls (kernel form 'c'): fluid cells with at least one wall
+// interface get flag 2 and are listed by padded offset, ascending; their ghost cells keep 0.
+// Plain host code (no CUDA calls), shared with tools/emu so that it is unit-tested on the CPU.
+inline void body_flags(const UniformGeom &g, const long long n_cells, const int *cell_ijk, const unsigned char *solved,
+                       const bool mark_walls, std::vector<unsigned char> &flag, std::vector<int> &walls)
+{
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    flag.assign((size_t) g.fs, 0);
+    walls.clear();
+    for (long long c = 0; c < n_cells; ++c) {
+        if (!solved[c]) flag[(size_t) uoff(g, cell_ijk[3 * c], cell_ijk[3 * c + 1], cell_ijk[3 * c + 2])] = 1;
+    }
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j) {
+            flag[(size_t) uoff(g, -1, j, k)] = flag[(size_t) uoff(g, 0, j, k)];
+            flag[(size_t) uoff(g, nx, j, k)] = flag[(size_t) uoff(g, nx - 1, j, k)];
+        }
+    for (int k = 0; k < nz; ++k)
+        for (int i = 0; i < nx; ++i) {
+            flag[(size_t) uoff(g, i, -1, k)] = flag[(size_t) uoff(g, i, 0, k)];
+            flag[(size_t) uoff(g, i, ny, k)] = flag[(size_t) uoff(g, i, ny - 1, k)];
+        }
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+            flag[(size_t) uoff(g, i, j, -1)] = flag[(size_t) uoff(g, i, j, 0)];
+            flag[(size_t) uoff(g, i, j, nz)] = flag[(size_t) uoff(g, i, j, nz - 1)];
+        }
+    if (!mark_walls) return;
+    const long long step[3] = { 1, g.px, (long long) g.py * g.px };
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                const long long o = uoff(g, i, j, k);
+                if (flag[(size_t) o] == 1) continue;
+                const int ijk[3] = { i, j, k }, ext[3] = { nx, ny, nz };
+                bool wall = false;
+                for (int a = 0; a < 3; ++a) {
+                    if (ijk[a] > 0 && flag[(size_t) (o - step[a])] == 1) wall = true;
+                    if (ijk[a] < ext[a] - 1 && flag[(size_t) (o + step[a])] == 1) wall = true;
+                }
+                if (wall) walls.push_back((int) o);
+            }
+    for (int o : walls) flag[(size_t) o] = 2;
 }
 
 } // namespace mmf

@@ -376,47 +376,10 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
     int rc = uniform_alloc(ctx, u);
     if (rc) return rc;
     if (bodies) {
-        // one flag per padded cell; the ghost shell repeats the cell it touches, so that the border interface of
-        // a cell that is not solved is skipped like the reference skips it (src/euler.cpp:181-183)
-        std::vector<unsigned char> flag((size_t) g.fs, 0);
-        for (int64_t c = 0; c < nc; ++c) {
-            if (!d->solved[c]) flag[(size_t) uoff(g, d->cell_ijk[3 * c], d->cell_ijk[3 * c + 1], d->cell_ijk[3 * c + 2])] = 1;
-        }
-        for (int k = 0; k < nz; ++k)
-            for (int j = 0; j < ny; ++j) {
-                flag[(size_t) uoff(g, -1, j, k)] = flag[(size_t) uoff(g, 0, j, k)];
-                flag[(size_t) uoff(g, nx, j, k)] = flag[(size_t) uoff(g, nx - 1, j, k)];
-            }
-        for (int k = 0; k < nz; ++k)
-            for (int i = 0; i < nx; ++i) {
-                flag[(size_t) uoff(g, i, -1, k)] = flag[(size_t) uoff(g, i, 0, k)];
-                flag[(size_t) uoff(g, i, ny, k)] = flag[(size_t) uoff(g, i, ny - 1, k)];
-            }
-        for (int j = 0; j < ny; ++j)
-            for (int i = 0; i < nx; ++i) {
-                flag[(size_t) uoff(g, i, j, -1)] = flag[(size_t) uoff(g, i, j, 0)];
-                flag[(size_t) uoff(g, i, j, nz)] = flag[(size_t) uoff(g, i, j, nz - 1)];
-            }
+        std::vector<unsigned char> flag;
+        std::vector<int> walls;
+        body_flags(g, nc, d->cell_ijk, d->solved, u->bodies_fixup, flag, walls);
         if (u->bodies_fixup) {
-            // fluid cells with a wall interface: flag 2, listed by padded offset (ascending: coalesced enough)
-            std::vector<int> walls;
-            const long long step[3] = { 1, g.px, (long long) g.py * g.px };
-            for (int k = 0; k < nz; ++k)
-                for (int j = 0; j < ny; ++j)
-                    for (int i = 0; i < nx; ++i) {
-                        const long long o = uoff(g, i, j, k);
-                        if (flag[(size_t) o] == 1) continue;
-                        const int ijk[3] = { i, j, k }, ext[3] = { nx, ny, nz };
-                        bool wall = false;
-                        for (int a = 0; a < 3; ++a) {
-                            if (ijk[a] > 0 && flag[(size_t) (o - step[a])] == 1) wall = true;
-                            if (ijk[a] < ext[a] - 1 && flag[(size_t) (o + step[a])] == 1) wall = true;
-                        }
-                        if (wall) walls.push_back((int) o);
-                    }
-            for (int o : walls) flag[(size_t) o] = 2;
-            // (the ghost shell was filled before: it repeats 0 / 1 of the cell it touches; a flag-2 border cell's
-            //  ghost stays 0, which is what the stage kernel's border interface needs)
             u->n_wall = (int) walls.size();
             if (walls.empty()) walls.push_back(0);
             if ((rc = dev_upload(ctx, &u->wall_list, walls))) return rc;

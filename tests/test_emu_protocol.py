@@ -195,3 +195,37 @@ def test_stage_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu
     assert bits_equal(ref[n + "/velocity"], P[:, 1:4])
     assert bits_equal(ref[n + "/pressure"], P[:, 0])
     assert bits_equal(ref[n + "/temperature"], P[:, 4])
+
+
+def test_host_side_body_flags_and_wall_list(emu, oracle):
+    """body_flags (uniform_device.cuh), the host code uniform_try_create runs for a box with bodies: flag array
+    with the replicated ghost shell and -- kernel form 'c' -- flag 2 plus the ascending list of fluid cells that
+    touch a wall, against the independent construction of the test harness (run_emu.Box)."""
+    import ctypes as C
+    I = C.POINTER(C.c_int)
+    meshes = [oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6], [5.6, 0.0, 5.1, 8.0, 1.4, 5.9]]),
+              with_bodies(lexicographic_box_mesh(33, 9, 5, 0.5, 0), [[-1, -1, -1, 1.2, 1.2, 1.2], [7.1, 2.1, 1.1, 7.4, 2.4, 1.4],
+                                                                     [10.1, 0.0, 0.0, 11.9, 9.0, 1.4], [12.6, 0.0, 0.0, 16.4, 2.4, 9.0]])]
+    for m in meshes:
+        m.setdefault("problem", "radsod")
+        box = run_emu.Box(emu, oracle, dict(m), 0)
+        nc = m["volume"].shape[0]
+        ijk = np.ascontiguousarray(m["cell_ijk"], np.int32)
+        solved = np.ascontiguousarray(m["solved"], np.uint8)
+        # inner cells and the ghosts behind a face; edge and corner ghosts touch no interface
+        px, py, pz = (int(v) for v in box.pad)
+        nx, ny, nz = (int(v) for v in box.dims)
+        kk, jj, ii = np.meshgrid(np.arange(pz) - 1, np.arange(py) - 1, np.arange(px) - 1, indexing="ij")
+        outside = ((ii < 0) | (ii >= nx)).astype(int) + ((jj < 0) | (jj >= ny)) + ((kk < 0) | (kk >= nz))
+        used = np.zeros(box.fs, bool)
+        used[:px * py * pz] = ((outside <= 1) & (ii <= nx) & (jj <= ny) & (kk <= nz)).reshape(-1)
+        for mark in (0, 1):
+            flag = np.full(box.fs, 255, np.uint8)
+            walls = np.zeros(nc, np.int32)
+            n = emu.emu_body_flags(box.dims.ctypes.data_as(I), nc, ijk.ctypes.data_as(I), solved.ctypes.data, mark,
+                                   flag.ctypes.data, walls.ctypes.data_as(I))
+            want = box.flag_c if mark else box.solid
+            assert np.array_equal(flag[used], want[used]) and flag.max() <= 2
+            assert n == (len(box.walls) if mark else 0)
+            if mark:
+                assert n > 20 and np.array_equal(walls[:n], box.walls)

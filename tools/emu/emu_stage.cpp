@@ -379,6 +379,24 @@ double emu_wall_cells(int stage, int order, const int dims[3], const int bc[6], 
     }
 }
 
+// body_flags (uniform_device.cuh: the host code uniform_try_create runs for a box with bodies) on a box of the
+// given extents; flag_out has room for fs bytes, walls_out for n_cells offsets; returns the number of wall cells
+int emu_body_flags(const int dims[3], long long n_cells, const int *cell_ijk, const unsigned char *solved, int mark_walls,
+                   unsigned char *flag_out, int *walls_out)
+{
+    UniformGeom g{};
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    int pad[3];
+    emu_padded(dims, pad, &g.fs);
+    g.px = pad[0]; g.py = pad[1]; g.pz = pad[2];
+    std::vector<unsigned char> flag;
+    std::vector<int> walls;
+    body_flags(g, n_cells, cell_ijk, solved, mark_walls != 0, flag, walls);
+    memcpy(flag_out, flag.data(), flag.size());
+    for (size_t q = 0; q < walls.size(); ++q) walls_out[q] = walls[q];
+    return (int) walls.size();
+}
+
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }
 
 // phase bookkeeping of the emulated mbarrier word (no fibers involved: arrivals only, waits inspected)
