@@ -1,15 +1,20 @@
 #!/bin/bash
 # First GPU call for the stage-kernel forms that were developed on the CPU emulator (tools/emu) and have
 # never run on a GPU: parity first, then the sweep that decides whether they become the default.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_first_call.sh'
+# (every step has its own, shorter timeout: a form that hangs on real hardware costs its own group only)
 # Everything lands in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 export MMF_TEST_EXPERIMENTAL=1
 # 1. parity of the experimental forms (d = plane-decoupled, h = + merged halo warp, w = + two y rows per warp, b / c = box with bodies), bounded
-timeout 600 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "fused_steps or bodies or primitives" > gpurun_out/experimental_parity.log 2>&1
-echo "parity exit code: $?" | tee -a gpurun_out/experimental_parity.log
-tail -5 gpurun_out/experimental_parity.log
+: > gpurun_out/experimental_parity.log
+for group in "fused_steps and (d12 or d16 or d8)" "fused_steps and (h12 or h16 or h8)" "fused_steps and w8" "bodies" "primitives"; do
+  echo "== $group" >> gpurun_out/experimental_parity.log
+  timeout 300 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "$group" >> gpurun_out/experimental_parity.log 2>&1
+  echo "parity [$group] exit code: $?" | tee -a gpurun_out/experimental_parity.log
+done
+grep -E "passed|failed|error|exit code" gpurun_out/experimental_parity.log | tail -12
 # 1b. the reference's own main on the new pieces: golden strings and bitwise reference fields (bodies included)
 #     with the body cases on the fused path and the writer's primitives from the device
 MMF_UNIFORM_BODIES=1 MMF_DEVICE_PRIMITIVES=1 timeout 600 python -m pytest tests/test_dropin_gpu.py tests/test_reference_fields_gpu.py -m gpu -x -q > gpurun_out/experimental_dropin.log 2>&1
