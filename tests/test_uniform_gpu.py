@@ -137,13 +137,6 @@ def _body_meshes(oracle):
     yield "box 37x29x11 + bodies", m
 
 
-def test_box_with_bodies_stays_on_the_generic_path_by_default(mmf, oracle, monkeypatch):
-    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
-    m = oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]])
-    with mmf.EulerSolver.from_mesh(m) as s:
-        assert s.info()["path"] == mmf.PATH_GENERIC
-
-
 @_exp
 @pytest.mark.parametrize("mode", ["1", "2"])
 def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch, mode):
@@ -278,7 +271,8 @@ def test_axis_order_flag_is_within_tolerance_not_exact(mmf, oracle):
         assert max_rel_diff(s.get_state(mmf.FIELD_U), Uo) <= 1e-12
 
 
-def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle):
+def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle, monkeypatch):
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)   # the fused body path is opt-in (forms b / c)
     boxes = np.array([[3.0, 3.0, 3.0, 5.0, 5.0, 5.0]])
     m = oracle.problem_mesh("radsod", 3, 16, boxes=boxes)
     with mmf.EulerSolver.from_mesh(m) as s:
