@@ -4,6 +4,7 @@
 
 #include "uniform_launch.cuh"
 #include "uniform_kernels.cuh"
+#include "uniform_eligibility.h"
 
 #include <algorithm>
 #include <cmath>
@@ -232,30 +233,6 @@ static int uniform_create(mmf_ctx *ctx, const mmf_uniform_desc *d)
     return uniform_alloc(ctx, u);
 }
 
-// Per-cell order in which the reference's interface loop touches the six faces, predicted from a
-// numbering convention; slots: 0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z.
-static void predicted_face_order(int numbering, const int ijk[3], int order[6])
-{
-    int n = 0;
-    int lows[3], keys[3], nl = 0;
-    for (int a = 0; a < 3; ++a) {
-        if (ijk[a] == 0) continue;
-        lows[nl] = a;
-        if (numbering == NUM_MORTON) keys[nl] = 3 * __builtin_ctz((unsigned) ijk[a]) + a;
-        else                         keys[nl] = a == 2 ? 2 : a == 1 ? 1 : 0; // lexicographic: z, y, x
-        nl++;
-    }
-    // descending key first
-    for (int a = 0; a < nl; ++a)
-        for (int b = a + 1; b < nl; ++b)
-            if (keys[b] > keys[a]) { std::swap(keys[a], keys[b]); std::swap(lows[a], lows[b]); }
-    for (int a = 0; a < nl; ++a) order[n++] = 2 * lows[a];
-    for (int a = 0; a < 3; ++a) {
-        if (ijk[a] == 0) order[n++] = 2 * a;
-        order[n++] = 2 * a + 1;
-    }
-}
-
 // Decide whether a host mesh description is a full, conforming, uniform 3-D box whose interface numbering
 // matches a known convention; if so build the uniform path from it.  All cells solved -- or, opt-in until the
 // kernel has run on the GPU (MMF_UNIFORM_BODIES=1), a box with bodies: cells that are not solved, and BC_WALL
@@ -263,99 +240,16 @@ static void predicted_face_order(int numbering, const int ijk[3], int order[6])
 static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
 {
     *used = false;
-    if (!d->cell_ijk || d->dim != 3 || (d->flags & MMF_FLAG_FORCE_GENERIC)) return MMF_OK;
-    const int nx = d->box_dims[0], ny = d->box_dims[1], nz = d->box_dims[2];
-    if (nx <= 0 || ny <= 0 || nz <= 0) return MMF_OK;
-    const int64_t nc = d->n_cells, nf = d->n_interfaces;
-    if ((int64_t) nx * ny * nz != nc) return MMF_OK;
-    for (int e = 0; e < 3; ++e) {
-        if (d->global_dims[e] != d->box_dims[e] || d->box_offset[e] != 0) return MMF_OK; // single-box only
-    }
-    const int64_t nf_expected = (int64_t) (nx + 1) * ny * nz + (int64_t) nx * (ny + 1) * nz + (int64_t) nx * ny * (nz + 1);
-    if (nf != nf_expected) return MMF_OK;
-    if (d->interface_order && d->n_interfaces_listed != nf) return MMF_OK;
-
-    // cells: a bijection onto the lattice, all internal, one volume; all solved unless bodies are allowed
+    // (bodies: opt-in until the kernels have run on the GPU, MMF_UNIFORM_BODIES=1 / 2; single GPU)
     const bool allow_bodies = getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) && !ctx->comm;
-    bool bodies = false;
-    std::vector<int64_t> lattice_to_raw((size_t) nc, -1);
-    const double V = d->volume[0];
-    for (int64_t c = 0; c < nc; ++c) {
-        const int i = d->cell_ijk[3 * c], j = d->cell_ijk[3 * c + 1], k = d->cell_ijk[3 * c + 2];
-        if (i < 0 || i >= nx || j < 0 || j >= ny || k < 0 || k >= nz) return MMF_OK;
-        const int64_t l = ((int64_t) k * ny + j) * nx + i;
-        if (lattice_to_raw[l] >= 0) return MMF_OK;
-        lattice_to_raw[l] = c;
-        if ((d->internal && !d->internal[c]) || d->volume[c] != V) return MMF_OK;
-        if (!d->solved[c]) {
-            if (!allow_bodies) return MMF_OK;
-            bodies = true;
-        }
-    }
-    const double A = d->area[0];
-    const double h = std::sqrt(A);
-
-    // interfaces: axis-aligned unit normals owner->neigh between lattice neighbours, one area,
-    // one BC per side; record for every cell the position of each of its six faces
-    std::vector<int64_t> face_pos((size_t) nc * 6, -1);
-    int bc_side[6] = { -9, -9, -9, -9, -9, -9 };
-    for (int64_t q = 0; q < nf; ++q) {
-        const int64_t f = d->interface_order ? d->interface_order[q] : q;
-        if (f < 0 || f >= nf) return MMF_OK;
-        const int64_t o = d->owner[f], n = d->neigh[f];
-        if (o < 0 || o >= nc || n >= nc || d->area[f] != A) return MMF_OK;
-        int axis = -1, sgn = 0;
-        for (int e = 0; e < 3; ++e) {
-            const double v = d->normal[3 * f + e];
-            if (v == 1.0 || v == -1.0) { if (axis >= 0) return MMF_OK; axis = e; sgn = (int) v; }
-            else if (v != 0.0) return MMF_OK;
-        }
-        if (axis < 0) return MMF_OK;
-        const int *oc = &d->cell_ijk[3 * o];
-        if (n >= 0) {
-            const int *ncell = &d->cell_ijk[3 * n];
-            for (int e = 0; e < 3; ++e) {
-                if (ncell[e] - oc[e] != (e == axis ? sgn : 0)) return MMF_OK;
-            }
-            const bool wall = (d->solved[o] != 0) != (d->solved[n] != 0);
-            if (d->bc[f] != (wall ? MMF_BC_WALL : MMF_BC_NONE)) return MMF_OK;
-            const int so = 2 * axis + (sgn > 0 ? 1 : 0), sn = 2 * axis + (sgn > 0 ? 0 : 1);
-            if (face_pos[o * 6 + so] >= 0 || face_pos[n * 6 + sn] >= 0) return MMF_OK;
-            face_pos[o * 6 + so] = q;
-            face_pos[n * 6 + sn] = q;
-        } else {
-            const int side = 2 * axis + (sgn > 0 ? 1 : 0);
-            const int lim = (axis == 0 ? nx : axis == 1 ? ny : nz) - 1;
-            if (oc[axis] != (sgn > 0 ? lim : 0)) return MMF_OK; // outward normal on the matching side
-            if (d->bc[f] < MMF_BC_FREE_FLOW || d->bc[f] > MMF_BC_DIRICHLET) return MMF_OK;
-            if (bc_side[side] == -9) bc_side[side] = d->bc[f];
-            else if (bc_side[side] != d->bc[f]) return MMF_OK;
-            if (face_pos[o * 6 + side] >= 0) return MMF_OK;
-            face_pos[o * 6 + side] = q;
-        }
-    }
-    for (size_t x = 0; x < face_pos.size(); ++x) if (face_pos[x] < 0) return MMF_OK;
-
-    // which numbering convention reproduces the host's per-cell interface order?
-    int numbering = -1;
-    for (int cand = 0; cand < 2 && numbering < 0; ++cand) {
-        bool ok = true;
-        for (int64_t c = 0; c < nc && ok; ++c) {
-            int order[6];
-            predicted_face_order(cand, &d->cell_ijk[3 * c], order);
-            for (int s = 0; s + 1 < 6; ++s) {
-                if (face_pos[c * 6 + order[s]] >= face_pos[c * 6 + order[s + 1]]) { ok = false; break; }
-            }
-        }
-        if (ok) numbering = cand;
-    }
-    int order_exact = 1;
-    if (numbering < 0) {
-        if (!(d->flags & MMF_FLAG_ORDER_AXIS)) return MMF_OK; // unknown order: stay on the exact generic path
-        numbering = NUM_AXIS;
-        order_exact = 0;
-    }
-    if (d->flags & MMF_FLAG_ORDER_AXIS) { numbering = NUM_AXIS; order_exact = 0; }
+    const UniformBoxAnalysis an = analyze_uniform_box(d, allow_bodies);
+    if (!an.eligible) return MMF_OK;
+    const int nx = d->box_dims[0], ny = d->box_dims[1], nz = d->box_dims[2];
+    const int64_t nc = d->n_cells;
+    const bool bodies = an.bodies;
+    const int numbering = an.numbering, order_exact = an.order_exact;
+    const int *bc_side = an.bc_side;
+    const double A = an.area, V = an.volume, h = an.h;
 
     UniformPath *u = new UniformPath();
     ctx->uni = u;

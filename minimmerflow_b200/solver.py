@@ -30,6 +30,51 @@ def selftest_division(n_samples=1 << 28, seed=12345, device=0):
     return bad.value
 
 
+def mesh_desc(mesh, flags=0, problem_type=0, dirichlet_info=None):
+    """mmf_mesh_desc of a host mesh mapping (see EulerSolver.from_mesh) plus the arrays it points into, which
+    the caller keeps alive for as long as the description is used."""
+    d = A.MeshDesc()
+    d.struct_size = C.sizeof(A.MeshDesc)
+    d.dim = int(mesh["dim"])
+    d.problem_type = int(problem_type)
+    d.flags = int(flags)
+    keep = {}
+    keep["owner"] = _as(mesh["owner"], np.int64)
+    keep["neigh"] = _as(mesh["neigh"], np.int64)
+    keep["bc"] = _as(mesh["bc"], np.int32)
+    keep["area"] = _as(mesh["area"], np.float64)
+    keep["normal"] = _as(mesh["normal"], np.float64)
+    keep["volume"] = _as(mesh["volume"], np.float64)
+    keep["solved"] = _as(mesh["solved"], np.uint8)
+    d.n_cells = keep["volume"].shape[0]
+    d.n_interfaces = keep["owner"].shape[0]
+    d.owner = _ptr(keep["owner"], C.c_int64)
+    d.neigh = _ptr(keep["neigh"], C.c_int64)
+    d.bc = _ptr(keep["bc"], C.c_int32)
+    d.area = _ptr(keep["area"], C.c_double)
+    d.normal = _ptr(keep["normal"], C.c_double)
+    d.volume = _ptr(keep["volume"], C.c_double)
+    d.solved = _ptr(keep["solved"], C.c_uint8)
+    if mesh.get("internal") is not None:
+        keep["internal"] = _as(mesh["internal"], np.uint8)
+        d.internal = _ptr(keep["internal"], C.c_uint8)
+    if mesh.get("interface_order") is not None:
+        keep["order"] = _as(mesh["interface_order"], np.int64)
+        d.interface_order = _ptr(keep["order"], C.c_int64)
+        d.n_interfaces_listed = keep["order"].shape[0]
+    if mesh.get("cell_ijk") is not None:
+        keep["ijk"] = _as(mesh["cell_ijk"], np.int32)
+        d.cell_ijk = _ptr(keep["ijk"], C.c_int32)
+        for e in range(3):
+            d.box_dims[e] = int(mesh["box_dims"][e])
+            d.global_dims[e] = int(mesh["box_dims"][e])
+            d.box_offset[e] = 0
+    if dirichlet_info is not None:
+        for k in range(A.N_FIELDS):
+            d.dirichlet_info[k] = float(dirichlet_info[k])
+    return d, keep
+
+
 class EulerSolver:
     """One GPU, one mesh (or one rank's partition)."""
 
@@ -46,45 +91,7 @@ class EulerSolver:
         dim, owner, neigh, bc, area, normal[nf,3], volume, solved and optionally internal,
         interface_order, cell_ijk + box_dims (structured hint)."""
         lib = A.load_library()
-        d = A.MeshDesc()
-        d.struct_size = C.sizeof(A.MeshDesc)
-        d.dim = int(mesh["dim"])
-        d.problem_type = int(problem_type)
-        d.flags = int(flags)
-        keep = {}
-        keep["owner"] = _as(mesh["owner"], np.int64)
-        keep["neigh"] = _as(mesh["neigh"], np.int64)
-        keep["bc"] = _as(mesh["bc"], np.int32)
-        keep["area"] = _as(mesh["area"], np.float64)
-        keep["normal"] = _as(mesh["normal"], np.float64)
-        keep["volume"] = _as(mesh["volume"], np.float64)
-        keep["solved"] = _as(mesh["solved"], np.uint8)
-        d.n_cells = keep["volume"].shape[0]
-        d.n_interfaces = keep["owner"].shape[0]
-        d.owner = _ptr(keep["owner"], C.c_int64)
-        d.neigh = _ptr(keep["neigh"], C.c_int64)
-        d.bc = _ptr(keep["bc"], C.c_int32)
-        d.area = _ptr(keep["area"], C.c_double)
-        d.normal = _ptr(keep["normal"], C.c_double)
-        d.volume = _ptr(keep["volume"], C.c_double)
-        d.solved = _ptr(keep["solved"], C.c_uint8)
-        if mesh.get("internal") is not None:
-            keep["internal"] = _as(mesh["internal"], np.uint8)
-            d.internal = _ptr(keep["internal"], C.c_uint8)
-        if mesh.get("interface_order") is not None:
-            keep["order"] = _as(mesh["interface_order"], np.int64)
-            d.interface_order = _ptr(keep["order"], C.c_int64)
-            d.n_interfaces_listed = keep["order"].shape[0]
-        if mesh.get("cell_ijk") is not None:
-            keep["ijk"] = _as(mesh["cell_ijk"], np.int32)
-            d.cell_ijk = _ptr(keep["ijk"], C.c_int32)
-            for e in range(3):
-                d.box_dims[e] = int(mesh["box_dims"][e])
-                d.global_dims[e] = int(mesh["box_dims"][e])
-                d.box_offset[e] = 0
-        if dirichlet_info is not None:
-            for k in range(A.N_FIELDS):
-                d.dirichlet_info[k] = float(dirichlet_info[k])
+        d, keep = mesh_desc(mesh, flags, problem_type, dirichlet_info)
         h = C.c_void_p()
         A.check(lib.mmf_create(C.byref(d), device, C.byref(h)))
         return cls(h, d.n_cells)

@@ -229,3 +229,51 @@ def test_host_side_body_flags_and_wall_list(emu, oracle):
             assert n == (len(box.walls) if mark else 0)
             if mark:
                 assert n > 20 and np.array_equal(walls[:n], box.walls)
+
+
+def test_dispatcher_decision_uniform_or_generic(emu, oracle):
+    """analyze_uniform_box (uniform_eligibility.h) -- what mmf_create decides between the fused uniform path and
+    the generic one -- on the CPU: numbering conventions, one BC per side, bodies only when allowed and only
+    with BC_WALL on exactly the fluid | solid interfaces, everything irregular to the generic path."""
+    import ctypes as C
+    from minimmerflow_b200.solver import mesh_desc
+    from common import two_level_mesh
+
+    def analyze(m, allow_bodies=0, flags=0):
+        d, keep = mesh_desc(m, flags=flags)
+        out = np.zeros(9, np.int32)
+        ok = emu.emu_analyze_box(C.addressof(d), allow_bodies, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return ok, out
+
+    ok, out = analyze(oracle.problem_mesh("vortex_xy", 3, 8))                    # the reference's numbering
+    assert ok and list(out[:3]) == [0, 1, 0] and list(out[3:]) == [0] * 6         # Morton, exact, free flow
+    ok, out = analyze(oracle.problem_mesh("radsod", 3, 8))
+    assert ok and list(out[3:]) == [1] * 6                                       # reflecting
+    ok, out = analyze(lexicographic_box_mesh(7, 5, 3, 0.5, 1))
+    assert ok and list(out[:3]) == [1, 1, 0]                                     # lexicographic
+    assert not analyze(oracle.problem_mesh("vortex_xy", 2, 8))[0]                # 2-D
+    assert not analyze(oracle.problem_mesh("vortex_xy", 3, 8), flags=1)[0]        # MMF_FLAG_FORCE_GENERIC
+    ok, out = analyze(oracle.problem_mesh("vortex_xy", 3, 8), flags=2)             # MMF_FLAG_ORDER_AXIS
+    assert ok and list(out[:2]) == [2, 0]
+    assert not analyze(two_level_mesh(3, 2, lambda i, j, k: i == 0))[0]          # hanging faces
+    # bodies
+    mb = oracle.problem_mesh("radsod", 3, 8, boxes=[[2.1, 2.1, 2.1, 5.9, 4.9, 3.9]])
+    assert not analyze(mb)[0]                                                    # not asked for: generic
+    ok, out = analyze(mb, allow_bodies=1)
+    assert ok and out[2] == 1
+    bad = dict(mb); bad["bc"] = mb["bc"].copy()
+    wall = np.nonzero(bad["bc"] == 2)[0][0]
+    bad["bc"][wall] = -1                                                         # a wall interface without BC_WALL
+    assert not analyze(bad, allow_bodies=1)[0]
+    bad["bc"][wall] = 2
+    inner = np.nonzero((mb["bc"] == -1) & (mb["neigh"] >= 0))[0][0]
+    bad["bc"][inner] = 2                                                         # BC_WALL between two fluid cells
+    assert not analyze(bad, allow_bodies=1)[0]
+    # an irregularity in an otherwise perfect box
+    m = oracle.problem_mesh("vortex_xy", 3, 8)
+    bad = dict(m); bad["volume"] = m["volume"].copy(); bad["volume"][5] *= 2
+    assert not analyze(bad)[0]
+    bad = dict(m); bad["bc"] = m["bc"].copy(); bad["bc"][np.nonzero(m["neigh"] < 0)[0][0]] = 1   # two BCs on one side
+    assert not analyze(bad)[0]
+    bad = dict(m); bad["interface_order"] = np.arange(m["owner"].shape[0])[::-1].copy()           # unknown order
+    assert not analyze(bad)[0]

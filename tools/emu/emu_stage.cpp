@@ -166,6 +166,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 #include "uniform_stage_v7.cuh"
 #include "uniform_stage_v5rb.cuh"
 #endif
+#include "uniform_eligibility.h"
 
 namespace {
 
@@ -395,6 +396,16 @@ int emu_body_flags(const int dims[3], long long n_cells, const int *cell_ijk, co
     memcpy(flag_out, flag.data(), flag.size());
     for (size_t q = 0; q < walls.size(); ++q) walls_out[q] = walls[q];
     return (int) walls.size();
+}
+
+// analyze_uniform_box (uniform_eligibility.h): the decision mmf_create takes between the fused uniform path
+// and the generic one.  out = { numbering, order_exact, bodies, bc_side[6] }; returns 1 if eligible.
+int emu_analyze_box(const mmf_mesh_desc *d, int allow_bodies, int out[9])
+{
+    const UniformBoxAnalysis r = analyze_uniform_box(d, allow_bodies != 0);
+    out[0] = r.numbering; out[1] = r.order_exact; out[2] = r.bodies ? 1 : 0;
+    for (int s = 0; s < 6; ++s) out[3 + s] = r.bc_side[s];
+    return r.eligible ? 1 : 0;
 }
 
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }

@@ -55,6 +55,8 @@ def load():
     lib.emu_set_spin_limit.argtypes = [C.c_longlong]
     lib.emu_set_xghost.argtypes = [_D, _D, C.c_longlong, C.c_int]
     lib.emu_set_solid.argtypes = [C.c_void_p]
+    lib.emu_analyze_box.restype = C.c_int
+    lib.emu_analyze_box.argtypes = [C.c_void_p, C.c_int, _I]
     lib.emu_body_flags.restype = C.c_int
     lib.emu_body_flags.argtypes = [_I, C.c_longlong, _I, C.c_void_p, C.c_int, C.c_void_p, _I]
     lib.emu_wall_cells.restype = C.c_double
