@@ -110,7 +110,8 @@ class ClockSampler(threading.Thread):
 def stage_kernel_label():
     """Name of the kernel that runs stages 2 and 3 (the dominant one), from the same knob the library reads."""
     names = {"p": "uniform_stage_kernel_v5", "r": "uniform_stage_kernel_v5r", "d": "uniform_stage_kernel_v6",
-             "h": "uniform_stage_kernel_v6 (merged halo warp)", "3": "uniform_stage_kernel_v3"}
+             "h": "uniform_stage_kernel_v6 (merged halo warp)", "w": "uniform_stage_kernel_v7 (two y rows per warp)",
+             "3": "uniform_stage_kernel_v3"}
     shapes = ["p16", "p16", "r12", "r12"]                      # library defaults (uniform_path.cuh)
     cfg = [c for c in os.environ.get("MMF_STAGE_CFG", "").split(":") if c]
     if len(cfg) == 1:

@@ -72,6 +72,57 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ S, int64_t 
     for (int k = 0; k < NF; ++k) u[k] = S[k * stride + c];
 }
 
+// The loop body of generic_rhs_kernel below as a function, for the fused stage kernel (generic_stage_kernel).  The
+// residual kernel keeps its own copy of the text on purpose: its SASS is the one the GPU parity runs validated.
+// One cell's residual: its interfaces in the reference's processing order, `-=` on the owner side and `+=` on
+// the neighbour side (src/euler.cpp:150-247); lmax = running maximum of the interface eigenvalues (:234).
+__device__ __forceinline__ void generic_cell_residual(const GenericMesh &m, const double *__restrict__ S, int64_t c,
+                                                      double *acc, double &lmax)
+{
+    const int64_t e0 = m.cf_ptr[c], e1 = m.cf_ptr[c + 1];
+    for (int64_t e = e0; e < e1; ++e) {
+        const int32_t ent  = m.cf_ent[e];
+        const int32_t f    = ent >> 1;
+        const int     side = ent & 1;
+        const int32_t o    = m.f_owner[f];
+        const int32_t nb   = m.f_neigh[f];
+        const int     bc   = m.f_bc[f];
+        const double  A    = m.f_area[f];
+        const double  nrm[3] = { m.f_normal[f], m.f_normal[m.n_ifaces + f], m.f_normal[2 * m.n_ifaces + f] };
+
+        double ownerRec[NF], neighRec[NF];
+        if (bc == BC_NONE) {
+            // order-1 reconstruction: face state = cell mean (src/reconstruction.cpp:90-97)
+            load_cell(S, m.stride, o, ownerRec);
+            load_cell(S, m.stride, nb, neighRec);
+        } else {
+            // src/euler.cpp:198-225: the fluid side is the owner when it is solved, otherwise
+            // the neighbour; the flipped normal is used for the BC evaluation only
+            const bool ownerSolved = m.c_solved[o] != 0;
+            if (ownerSolved) {
+                load_cell(S, m.stride, o, ownerRec);
+                interface_bc_values(bc, nrm, m.dirichlet_info, ownerRec, neighRec);
+            } else {
+                const double flipped[3] = { -1. * nrm[0], -1. * nrm[1], -1. * nrm[2] };
+                load_cell(S, m.stride, nb, neighRec);
+                interface_bc_values(bc, flipped, m.dirichlet_info, neighRec, ownerRec);
+            }
+        }
+
+        double flux[NF], lambda;
+        eval_splitting(ownerRec, neighRec, nrm, flux, &lambda); // un-flipped normal (:232)
+        lmax = (lambda < lmax) ? lmax : lambda;                  // :234
+
+        if (side == 0) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) acc[k] -= A * flux[k];  // :237-241
+        } else {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) acc[k] += A * flux[k];  // :243-247
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) generic_rhs_kernel(GenericMesh m, const double *__restrict__ S,
                                                           double *__restrict__ RHS, double *__restrict__ max_eig)
 {
@@ -160,6 +211,46 @@ __global__ void __launch_bounds__(256) generic_rk_kernel(int64_t n_cells, int64_
             U[i] = (1. / 3) * U[i] + (2. / 3) * (W[i] + q);
         }
     }
+}
+
+// Residual and RK stage in one pass for stages 2 and 3 (opt-in, MMF_GENERIC_FUSED=1): every thread forms its
+// cell's residual exactly like generic_rhs_kernel and applies the stage loop of src/main.cpp:445-459 / 481-495
+// to it right away, so the residual is neither written nor read back between the two.  Stage 1 stays unfused:
+// its dt is chosen from its own residual's face maximum (src/main.cpp:398-402).
+//   stage 2: Out = the other work array (neighbours still read Sin); cells the loop skips carry Sin over
+//   stage 3: Out = Un = U, in place (a cell's U^n is read by that cell only); the residual is ALSO stored,
+//            because cellRHS of the reference holds the stage-3 residual when a step ends (it is written
+//            out with the solution, src/main.cpp:284-298)
+// A step switched off on the device (ctl->active == 0) updates nothing, like generic_rk_kernel.
+template <int STAGE>
+__global__ void __launch_bounds__(128) generic_stage_kernel(GenericMesh m, const double *__restrict__ Sin,
+                                                            const double *Un, double *Out, double *__restrict__ RHS,
+                                                            const StepControl *__restrict__ ctl,
+                                                            double *__restrict__ max_eig)
+{
+    static_assert(STAGE == 2 || STAGE == 3, "fused generic stages are 2 and 3");
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double lmax = 0.0;
+    if (c < m.n_cells) {
+        double acc[NF] = { 0., 0., 0., 0., 0. };
+        generic_cell_residual(m, Sin, c, acc, lmax);
+        const bool upd = ctl->active != 0.0 && m.c_update[c];
+        const double dt = ctl->dt;
+        const double V  = m.c_volume[c];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) {
+            const int64_t i = k * m.stride + c;
+            if (STAGE == 3) RHS[i] = acc[k];
+            if (upd) {
+                const double q = dt * acc[k] / V;
+                if (STAGE == 2) Out[i] = 0.75 * Un[i] + 0.25 * (Sin[i] + q);
+                else            Out[i] = (1. / 3) * Un[i] + (2. / 3) * (Sin[i] + q);
+            } else if (STAGE == 2) {
+                Out[i] = Sin[i];
+            }
+        }
+    }
+    block_max_to_global(lmax, max_eig);
 }
 
 // Runs after the stage-1 residual: `while (t < tMax)` test (src/main.cpp:377) and the dt choice

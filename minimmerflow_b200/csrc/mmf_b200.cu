@@ -2,6 +2,7 @@
 // generic (connectivity-driven) path.  Host code is C++17; all numerical work happens in the
 // sm_100a kernels of generic_kernels.cuh / uniform_path.cuh.  There is no CPU fallback.
 #include "mmf_common.cuh"
+#include "generic_tables.h"
 #include "uniform_path.cuh"
 #include "comm.cuh"
 
@@ -70,68 +71,24 @@ static int validate_desc(const mmf_mesh_desc *d)
 
 static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
 {
-    const int64_t nc = d->n_cells, nf = d->n_interfaces;
-    const int64_t n_listed = d->interface_order ? d->n_interfaces_listed : nf;
-
-    // per-interface tables (raw id indexed)
-    std::vector<int32_t> owner(nf), neigh(nf);
-    std::vector<int8_t> bc(nf);
-    std::vector<double> normal(3 * (size_t) nf);
-    for (int64_t f = 0; f < nf; ++f) {
-        if (d->owner[f] < 0 || d->owner[f] >= nc || d->neigh[f] >= nc) {
-            return fail(ctx, MMF_ERR_INVALID, "mmf_create: interface %lld has owner/neigh out of range",
-                        (long long) f);
-        }
-        owner[f] = (int32_t) d->owner[f];
-        neigh[f] = d->neigh[f] < 0 ? -1 : (int32_t) d->neigh[f];
-        if (d->bc[f] < MMF_BC_NONE || d->bc[f] > MMF_BC_DIRICHLET) {
-            return fail(ctx, MMF_ERR_INVALID, "mmf_create: interface %lld has unknown BC code %d",
-                        (long long) f, d->bc[f]);
-        }
-        if (neigh[f] < 0 && d->bc[f] == MMF_BC_NONE) {
-            return fail(ctx, MMF_ERR_INVALID, "mmf_create: border interface %lld has BC_NONE", (long long) f);
-        }
-        bc[f] = (int8_t) d->bc[f];
-        for (int e = 0; e < 3; ++e) normal[(size_t) e * nf + f] = d->normal[3 * f + e];
-    }
-
-    // cell -> interface lists in processing order (counting sort keeps the order)
-    std::vector<uint8_t> solved(nc), update(nc);
-    for (int64_t c = 0; c < nc; ++c) {
-        solved[c] = d->solved[c] ? 1 : 0;
-        update[c] = (solved[c] && (!d->internal || d->internal[c])) ? 1 : 0;
-    }
-    std::vector<int64_t> ptr(nc + 1, 0);
-    auto processed = [&](int64_t f, bool &oS, bool &nS) {
-        oS = solved[owner[f]] != 0;
-        nS = neigh[f] >= 0 && solved[neigh[f]] != 0;
-        return oS || nS; // src/euler.cpp:181-183
-    };
-    for (int64_t q = 0; q < n_listed; ++q) {
-        const int64_t f = d->interface_order ? d->interface_order[q] : q;
-        if (f < 0 || f >= nf) return fail(ctx, MMF_ERR_INVALID, "mmf_create: interface_order[%lld] out of range", (long long) q);
-        bool oS, nS;
-        if (!processed(f, oS, nS)) continue;
-        if (oS) ptr[owner[f] + 1]++;
-        if (nS) ptr[neigh[f] + 1]++;
-    }
-    for (int64_t c = 0; c < nc; ++c) ptr[c + 1] += ptr[c];
-    std::vector<int32_t> ent((size_t) ptr[nc]);
+    // the tables themselves are host logic without a device: generic_tables.h (unit-tested on the CPU)
+    GenericTables t;
     {
-        std::vector<int64_t> cursor(ptr.begin(), ptr.end() - 1);
-        for (int64_t q = 0; q < n_listed; ++q) {
-            const int64_t f = d->interface_order ? d->interface_order[q] : q;
-            bool oS, nS;
-            if (!processed(f, oS, nS)) continue;
-            if (oS) ent[(size_t) cursor[owner[f]]++] = (int32_t) (f << 1);
-            if (nS) ent[(size_t) cursor[neigh[f]]++] = (int32_t) ((f << 1) | 1);
-        }
+        std::string err;
+        const int trc = build_generic_tables(d, t, err);
+        if (trc) return fail(ctx, trc, "%s", err.c_str());
     }
+    const int64_t nc = t.n_cells, nf = t.n_ifaces;
+    const std::vector<int32_t> &owner = t.owner, &neigh = t.neigh, &ent = t.ent;
+    const std::vector<int8_t> &bc = t.bc;
+    const std::vector<double> &normal = t.normal, &area = t.area, &volume = t.volume;
+    const std::vector<uint8_t> &solved = t.solved, &update = t.update;
+    const std::vector<int64_t> &ptr = t.ptr;
 
     GenericMesh &g = ctx->gm;
     g.n_cells  = nc;
     g.n_ifaces = nf;
-    g.stride   = (nc + 31) / 32 * 32;
+    g.stride   = t.stride;
     memcpy(g.dirichlet_info, d->dirichlet_info, sizeof g.dirichlet_info);
 
     int rc;
@@ -142,7 +99,6 @@ static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
     if ((rc = dev_upload(ctx, &d_owner, owner))) return rc;
     if ((rc = dev_upload(ctx, &d_neigh, neigh))) return rc;
     if ((rc = dev_upload(ctx, &d_bc, bc))) return rc;
-    const std::vector<double> area(d->area, d->area + nf), volume(d->volume, d->volume + nc);
     if ((rc = dev_upload(ctx, &d_area, area))) return rc;
     if ((rc = dev_upload(ctx, &d_normal, normal))) return rc;
     if ((rc = dev_upload(ctx, &d_vol, volume))) return rc;
@@ -154,6 +110,11 @@ static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
     for (int i = 0; i < 3; ++i) {
         if ((rc = dev_alloc(ctx, &ctx->fields[i], (size_t) NF * g.stride))) return rc;
         MMF_CUDA(ctx, cudaMemset(ctx->fields[i], 0, sizeof(double) * NF * g.stride));
+    }
+    ctx->generic_fused = getenv("MMF_GENERIC_FUSED") && atoi(getenv("MMF_GENERIC_FUSED")) != 0;
+    if (ctx->generic_fused) {
+        if ((rc = dev_alloc(ctx, &ctx->w_alt, (size_t) NF * g.stride))) return rc;
+        MMF_CUDA(ctx, cudaMemset(ctx->w_alt, 0, sizeof(double) * NF * g.stride));
     }
     ctx->path = MMF_PATH_GENERIC;
     return MMF_OK;
@@ -401,6 +362,23 @@ static int rk_enqueue(mmf_ctx *ctx, int stage)
     return MMF_OK;
 }
 
+// stages 2 and 3 of the generic path as one kernel each (MMF_GENERIC_FUSED=1)
+static int generic_stage_enqueue(mmf_ctx *ctx, int stage)
+{
+    double *d_max = &ctx->d_ctl->max_eig[stage - 1];
+    MMF_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(double), ctx->stream));
+    double *U = ctx->fields[MMF_FIELD_U], *W = ctx->fields[MMF_FIELD_W], *R = ctx->fields[MMF_FIELD_RHS];
+    const unsigned grid = grid_for(ctx->n_cells, 128);
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        if (stage == 2) generic_stage_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, ctx->w_alt, R, ctx->d_ctl, d_max);
+        else            generic_stage_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, U, R, ctx->d_ctl, d_max);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    if (stage == 2) std::swap(ctx->fields[MMF_FIELD_W], ctx->w_alt); // field W is what stage 2 wrote
+    return MMF_OK;
+}
+
 extern "C" int mmf_compute_rhs(mmf_ctx *ctx, int field, int order, double *max_eig)
 {
     int rc = check_field(ctx, field, "mmf_compute_rhs");
@@ -469,11 +447,17 @@ static int step_enqueue(mmf_ctx *ctx)
     MMF_LAUNCH_CHECK(ctx);
     if ((rc = rk_enqueue(ctx, 1))) return rc;
     if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_W))) return rc;
-    if ((rc = rhs_enqueue(ctx, MMF_FIELD_W, 1))) return rc;
-    if ((rc = rk_enqueue(ctx, 2))) return rc;
-    if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_W))) return rc;
-    if ((rc = rhs_enqueue(ctx, MMF_FIELD_W, 2))) return rc;
-    if ((rc = rk_enqueue(ctx, 3))) return rc;
+    if (ctx->generic_fused) { // residual + stage update in one kernel for stages 2 and 3 (generic_stage_kernel)
+        if ((rc = generic_stage_enqueue(ctx, 2))) return rc;
+        if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_W))) return rc;
+        if ((rc = generic_stage_enqueue(ctx, 3))) return rc;
+    } else {
+        if ((rc = rhs_enqueue(ctx, MMF_FIELD_W, 1))) return rc;
+        if ((rc = rk_enqueue(ctx, 2))) return rc;
+        if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_W))) return rc;
+        if ((rc = rhs_enqueue(ctx, MMF_FIELD_W, 2))) return rc;
+        if ((rc = rk_enqueue(ctx, 3))) return rc;
+    }
     if (ctx->comm && (rc = comm_exchange_enqueue(ctx, MMF_FIELD_U))) return rc;
     if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[1], 2))) return rc; // logged only (:436, :472)
     advance_time_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl, 0);

@@ -8,7 +8,14 @@ import pytest
 import oracle_lib
 from common import bits_equal, golden_cases, lexicographic_box_mesh, max_rel_diff, two_level_mesh
 
+import os
+
 pytestmark = pytest.mark.gpu
+
+# MMF_GENERIC_FUSED=1 (stages 2 and 3 as one kernel each, generic_stage_kernel) has been checked on the CPU
+# emulator only (tests/test_emu_generic.py): opt-in until its first GPU run, like the unmeasured stage-kernel forms
+EXPERIMENTAL = os.environ.get("MMF_TEST_EXPERIMENTAL", "0") not in ("", "0")
+_exp = pytest.mark.skipif(not EXPERIMENTAL, reason="generic fused stages: set MMF_TEST_EXPERIMENTAL=1")
 
 GENERIC = 1  # MMF_FLAG_FORCE_GENERIC
 
@@ -211,3 +218,38 @@ def test_run_respects_max_steps_and_tmax_clamp(mmf, oracle):
         assert steps2 == 1 and t2 == t + 1e-3
         ref = oracle.run("radsod", 2, 32, t_end=1.0e30, max_steps=7, want_state=True)
     assert ref["t"] == t
+
+
+@_exp
+@pytest.mark.parametrize("kind", ["vortex2d", "bodies3d", "hanging3d"])
+def test_generic_fused_stages_bit_exact(mmf, oracle, monkeypatch, kind):
+    """MMF_GENERIC_FUSED=1: residual + RK update of stages 2 and 3 in one kernel each, two work arrays swapping
+    roles; dt, the three logged eigenvalues, U, W and the stage-3 residual left in RHS are those of the oracle."""
+    monkeypatch.setenv("MMF_GENERIC_FUSED", "1")
+    if kind == "vortex2d":
+        m = oracle.problem_mesh("vortex_xy", 2, 64)
+        U = oracle.init_state(m)
+    elif kind == "bodies3d":
+        m = oracle.problem_mesh("radsod", 3, 16, boxes=np.array([[2.9, 2.9, 2.9, 5.1, 5.1, 5.1], [0.0, 6.0, 0.0, 1.2, 8.0, 8.0]]))
+        U = oracle.init_state(m)
+    else:
+        m = two_level_mesh(3, 6, lambda i, j, k: (1 <= i < 4 and 2 <= j < 5 and k < 3) or (i + j + k) % 5 == 0)
+        m["problem"] = "radsod"
+        nc = m["volume"].shape[0]
+        rng = np.random.default_rng(11)
+        rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-0.4, 0.4, (nc, 3)); p = rng.uniform(0.6, 1.4, nc)
+        U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+    with _solver(mmf, m) as s:
+        assert s.info()["path"] == mmf.PATH_GENERIC
+        s.set_state(mmf.FIELD_U, U)
+        s.set_state(mmf.FIELD_W, U)
+        Uo, Wo, Ro = U.copy(), U.copy(), np.zeros_like(U)
+        t = 0.0
+        for _ in range(6):
+            dt, me3 = oracle.step(m, 0.45, t, 10.0, Uo, Wo, Ro)
+            dtg, meg = s.step(0.45, float(m["size"].min()), t, 10.0)
+            assert dtg == dt and list(me3) == meg
+            t += dt
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+        assert bits_equal(s.get_state(mmf.FIELD_W), Wo)
+        assert bits_equal(s.get_state(mmf.FIELD_RHS), Ro)

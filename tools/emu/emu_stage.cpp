@@ -1,6 +1,12 @@
 // tools/emu/emu_stage.cpp -- DEVELOPMENT TOOL (see shim/cuda_runtime.h): the fiber runtime and a C entry
 // point that runs ONE launch of a fused stage kernel, compiled from the product's kernel source, on padded
 // host arrays.  tools/emu/run_emu.py drives it and compares with the CPU oracle.
+// standard headers that spell attributes the shim's CUDA keywords would rewrite come first
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
 #include <cuda_runtime.h>
 
 #include <sys/mman.h>
@@ -167,6 +173,8 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 #include "uniform_stage_v5rb.cuh"
 #endif
 #include "uniform_eligibility.h"
+#include "generic_kernels.cuh"
+#include "generic_tables.h"
 
 namespace {
 
@@ -406,6 +414,88 @@ int emu_analyze_box(const mmf_mesh_desc *d, int allow_bodies, int out[9])
     out[0] = r.numbering; out[1] = r.order_exact; out[2] = r.bodies ? 1 : 0;
     for (int s = 0; s < 6; ++s) out[3 + s] = r.bc_side[s];
     return r.eligible ? 1 : 0;
+}
+
+// ---- the generic path ------------------------------------------------------------------------------------
+// cell -> interface lists of a host mesh description (generic_tables.h: what create_generic uploads).  ptr_out
+// has room for n_cells + 1 entries, ent_out for two per interface (either may be null); returns the number of
+// entries or -1 (message in err).
+long long emu_generic_tables(const mmf_mesh_desc *d, long long *ptr_out, int *ent_out, unsigned char *update_out, char *err,
+                             int err_len)
+{
+    GenericTables t;
+    std::string msg;
+    if (build_generic_tables(d, t, msg)) {
+        if (err && err_len > 0) snprintf(err, (size_t) err_len, "%s", msg.c_str());
+        return -1;
+    }
+    if (ptr_out) for (size_t c = 0; c < t.ptr.size(); ++c) ptr_out[c] = t.ptr[c];
+    if (ent_out) for (size_t e = 0; e < t.ent.size(); ++e) ent_out[e] = t.ent[e];
+    if (update_out) memcpy(update_out, t.update.data(), t.update.size());
+    return (long long) t.ent.size();
+}
+
+long long emu_generic_stride(long long n_cells) { return (n_cells + 31) / 32 * 32; }
+
+// Steps of the generic path, the kernel sequence of step_enqueue (mmf_b200.cu) run on the emulator: the
+// product's generic kernels, compiled from their source, on SoA arrays [field * stride + cell] the caller
+// provides (stride = emu_generic_stride).  fused = 0: residual and RK kernels of every stage; fused = 1: stages 2
+// and 3 by generic_stage_kernel with the two work arrays swapping roles -- on return W is whichever array the
+// last stage 2 wrote, copied back into the caller's W.  One warp per block here (the block-wide maximum is
+// order independent; the tool's `__shared__` is per lane, which a one-warp block never notices).
+// Loop: `while (t < t_max)` and at most max_steps (< 0: unbounded) like mmf_run.  Returns the steps taken.
+int emu_generic_run(const mmf_mesh_desc *d, int fused, double *U, double *W, double *RHS, double cfl, double min_h,
+                    double *t, double t_max, int max_steps, double *dt_last, double eig_last[3])
+{
+    GenericTables tb;
+    std::string msg;
+    if (build_generic_tables(d, tb, msg)) return -1;
+    GenericMesh m{};
+    m.n_cells = tb.n_cells; m.n_ifaces = tb.n_ifaces; m.stride = tb.stride;
+    m.cf_ptr = tb.ptr.data(); m.cf_ent = tb.ent.data();
+    m.f_owner = tb.owner.data(); m.f_neigh = tb.neigh.data(); m.f_bc = tb.bc.data();
+    m.f_area = tb.area.data(); m.f_normal = tb.normal.data();
+    m.c_solved = tb.solved.data(); m.c_update = tb.update.data(); m.c_volume = tb.volume.data();
+    memcpy(m.dirichlet_info, d->dirichlet_info, sizeof m.dirichlet_info);
+
+    StepControl ctl{};
+    ctl.t = *t; ctl.t_max = t_max; ctl.cfl = cfl; ctl.min_h = min_h;
+    std::vector<double> alt((size_t) NF * m.stride, 0.0);
+    double *Wc = W, *Wa = alt.data();
+    const unsigned grid = (unsigned) ((m.n_cells + 31) / 32);
+    emu::g_chaos = 0;
+    auto run = [&](const std::function<void()> &body) { emu::launch(grid, 1, 1, 32, mmf::smem, 0, body, 1u); };
+    auto rhs = [&](const double *S, int slot) {
+        ctl.max_eig[slot] = 0.0;
+        double *mx = &ctl.max_eig[slot];
+        run([=] { generic_rhs_kernel(m, S, RHS, mx); });
+    };
+    StepControl *c = &ctl;
+    int steps = 0;
+    while (ctl.t < t_max && (max_steps < 0 || steps < max_steps)) {
+        rhs(U, 0);
+        choose_dt_kernel(c);
+        run([=] { generic_rk_kernel<1>(m.n_cells, m.stride, m.c_update, m.c_volume, c, U, Wc, RHS); });
+        if (fused) {
+            ctl.max_eig[1] = 0.0;
+            { double *mx = &ctl.max_eig[1]; double *Si = Wc, *So = Wa; run([=] { generic_stage_kernel<2>(m, Si, U, So, RHS, c, mx); }); }
+            std::swap(Wc, Wa);
+            ctl.max_eig[2] = 0.0;
+            { double *mx = &ctl.max_eig[2]; double *Si = Wc; run([=] { generic_stage_kernel<3>(m, Si, U, U, RHS, c, mx); }); }
+        } else {
+            rhs(Wc, 1);
+            run([=] { generic_rk_kernel<2>(m.n_cells, m.stride, m.c_update, m.c_volume, c, U, Wc, RHS); });
+            rhs(Wc, 2);
+            run([=] { generic_rk_kernel<3>(m.n_cells, m.stride, m.c_update, m.c_volume, c, U, Wc, RHS); });
+        }
+        advance_time_kernel(c, 0);
+        ++steps;
+    }
+    if (Wc != W) memcpy(W, Wc, sizeof(double) * (size_t) NF * m.stride);
+    *t = ctl.t;
+    if (dt_last) *dt_last = ctl.dt;
+    if (eig_last) for (int i = 0; i < 3; ++i) eig_last[i] = ctl.max_eig[i];
+    return steps;
 }
 
 void emu_set_spin_limit(long long n) { emu::g_spin_limit = n; }

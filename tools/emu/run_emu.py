@@ -31,7 +31,7 @@ _I = C.POINTER(C.c_int)
 
 def build(force=False):
     srcs = [os.path.join(HERE, f) for f in ("emu_stage.cpp", "emu_ptx_helpers.h", "shim/cuda_runtime.h")]
-    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh") or f.endswith(".h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -64,6 +64,12 @@ def load():
                                    C.c_double, _D]
     lib.emu_eig_body.restype = C.c_double
     lib.emu_eig_body.argtypes = [_I, _I, _D, C.c_void_p]
+    lib.emu_generic_tables.restype = C.c_longlong
+    lib.emu_generic_tables.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), _I, C.c_void_p, C.c_char_p, C.c_int]
+    lib.emu_generic_stride.restype = C.c_longlong
+    lib.emu_generic_stride.argtypes = [C.c_longlong]
+    lib.emu_generic_run.restype = C.c_int
+    lib.emu_generic_run.argtypes = [C.c_void_p, C.c_int, _D, _D, _D, C.c_double, C.c_double, _D, C.c_double, C.c_int, _D, _D]
     return lib
 
 

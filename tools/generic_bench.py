@@ -48,7 +48,8 @@ def main():
             s.run(0.45, m["h"], 0.0, 1e30, max_steps=args.steps)
             ms = s.timer_stop()
             out[name] = s.get_state(mmf.FIELD_U)
-            print(json.dumps({"path": name, "path_code": path, "bodies_mode": os.environ.get("MMF_UNIFORM_BODIES", "") if args.bodies else "", "cells": cells, "solved_cells": int(m["solved"].sum()),
+            print(json.dumps({"path": name, "path_code": path, "bodies_mode": os.environ.get("MMF_UNIFORM_BODIES", "") if args.bodies else "",
+                              "generic_fused": os.environ.get("MMF_GENERIC_FUSED", "0"), "cells": cells, "solved_cells": int(m["solved"].sum()),
                               "ms_per_step": ms / args.steps,
                               "cell_updates_per_s": int(m["solved"].sum()) * 3 * args.steps / (ms * 1e-3)}), flush=True)
     print(json.dumps({"bitwise_equal": bool(np.array_equal(out["uniform"], out["generic"]))}))

@@ -14,7 +14,10 @@ for group in "fused_steps and (d12 or d16 or d8)" "fused_steps and (h12 or h16 o
   timeout 300 python -m pytest tests/test_uniform_gpu.py -m gpu -x -q -k "$group" >> gpurun_out/experimental_parity.log 2>&1
   echo "parity [$group] exit code: $?" | tee -a gpurun_out/experimental_parity.log
 done
-grep -E "passed|failed|error|exit code" gpurun_out/experimental_parity.log | tail -12
+echo "== generic fused stages" >> gpurun_out/experimental_parity.log
+timeout 300 python -m pytest tests/test_generic_gpu.py -m gpu -x -q -k generic_fused >> gpurun_out/experimental_parity.log 2>&1
+echo "parity [generic fused stages] exit code: $?" | tee -a gpurun_out/experimental_parity.log
+grep -E "passed|failed|error|exit code" gpurun_out/experimental_parity.log | tail -14
 # 1b. the reference's own main on the new pieces: golden strings and bitwise reference fields (bodies included)
 #     with the body cases on the fused path and the writer's primitives from the device
 MMF_UNIFORM_BODIES=1 MMF_DEVICE_PRIMITIVES=1 timeout 600 python -m pytest tests/test_dropin_gpu.py tests/test_reference_fields_gpu.py -m gpu -x -q > gpurun_out/experimental_dropin.log 2>&1
@@ -28,7 +31,10 @@ for lz in 26 32 43 52 64; do
   timeout 300 python tools/stage_sweep.py --size 256 --steps 6 --variants "p16:p16:h12:h12@$lz,p16:p16:w8:w8@$lz,p16:p16:d12:d12@$lz,p16:p16:r12:r12@$lz" >> gpurun_out/stage_sweep_lz.jsonl 2>> gpurun_out/stage_sweep_256.err
 done
 cat gpurun_out/stage_sweep_lz.jsonl
-timeout 600 python tools/generic_bench.py --size 128 --steps 6 > gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err; cat gpurun_out/generic_bench_128.jsonl
+timeout 600 python tools/generic_bench.py --size 128 --steps 6 > gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err
+# the same with stages 2 and 3 of the generic path fused (generic_stage_kernel)
+MMF_GENERIC_FUSED=1 timeout 600 python tools/generic_bench.py --size 128 --steps 6 >> gpurun_out/generic_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err
+cat gpurun_out/generic_bench_128.jsonl
 # 4. a box with bodies: fused uniform path (form b, MMF_UNIFORM_BODIES=1) against the generic path
 for mode in 1 2; do
   MMF_UNIFORM_BODIES=$mode timeout 600 python tools/generic_bench.py --size 128 --steps 6 --bodies >> gpurun_out/body_bench_128.jsonl 2>> gpurun_out/stage_sweep_256.err
