@@ -72,53 +72,124 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ S, int64_t 
     for (int k = 0; k < NF; ++k) u[k] = S[k * stride + c];
 }
 
-// The loop body of generic_rhs_kernel below as a function, for the fused stage kernel (generic_stage_kernel).  The
-// residual kernel keeps its own copy of the text on purpose: its SASS is the one the GPU parity runs validated.
+// ---- one cell's residual with the cell's own derived state computed ONCE ------------------------------------
+// In generic_rhs_kernel below every interface converts both of its cells to primitives (euler::evalSplitting,
+// src/euler.cpp:42-73): a cell is converted once per interface it touches.  The cell a thread gathers for is a
+// side of every interface in its list, so the fused stage kernel (generic_stage_kernel) derives it once --
+// primitives (src/utils.cpp:48-63), sound speed, |v|^2 and total energy as src/euler.cpp:52-58, 83-92 form them
+// -- and per interface derives the other side only.  Same inputs, same operations, same order => the same bits
+// (checked against the oracle on the emulator, tests/test_emu_generic.py); about a third fewer FP64
+// instructions per cell.  generic_rhs_kernel keeps the reference-shaped text: its SASS is the one the GPU parity
+// runs validated.
+struct DerivedCell {
+    double cons[NF], prim[NF];
+    double a;    // sqrt(GAMMA * T)                   (src/euler.cpp:54, :58)
+    double vel2; // u*u + v*v + w*w                   (src/euler.cpp:89)
+    double eto;  // p / (GAMMA-1) + 0.5 * rho * vel2   (src/euler.cpp:103)
+};
+
+__device__ __forceinline__ void derive_cell_generic(DerivedCell &d)
+{
+    conservative2primitive(d.cons, d.prim);
+    d.a = sqrt(GAMMA * d.prim[FID_T]);
+    const double u = d.prim[FID_U], v = d.prim[FID_V], w = d.prim[FID_W];
+    d.vel2 = u * u + v * v + w * w;
+    d.eto  = d.prim[FID_P] / GM1 + 0.5 * d.cons[FID_RHO] * d.vel2;
+}
+
+// euler::evalFluxes (src/euler.cpp:83-113) from a derived cell; un is the normal velocity evalSplitting
+// evaluates a second time with the same operands (src/euler.cpp:52, :56)
+__device__ __forceinline__ void fluxes_of_derived(const DerivedCell &d, const double *n, double *flux, double *un_out)
+{
+    const double un = normal_velocity(d.prim, n);
+    const double p  = d.prim[FID_P];
+    const double massFlux = d.cons[FID_RHO] * un;
+    flux[0] = massFlux;
+    flux[1] = massFlux * d.prim[FID_U] + p * n[0];
+    flux[2] = massFlux * d.prim[FID_V] + p * n[1];
+    flux[3] = massFlux * d.prim[FID_W] + p * n[2];
+    flux[4] = un * (d.eto + p);
+    *un_out = un;
+}
+
+// euler::evalInterfaceBCValues (src/euler.cpp:261-376) from the derived inner cell: the reflecting / wall branch
+// starts from the inner cell's primitives (:326), which are the ones already held
+__device__ __forceinline__ void bc_values_of_derived(int bc, const double *normal, const double *dirichlet_info,
+                                                     const DerivedCell &in, double *cons_bc)
+{
+    if (bc == BC_FREE_FLOW) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) cons_bc[k] = in.cons[k];
+    } else if (bc == BC_REFLECTING || bc == BC_WALL) {
+        double prim[NF];
+        const double un = normal_velocity(in.prim, normal);
+        const double n0 = un * normal[0], n1 = un * normal[1], n2 = un * normal[2];
+        prim[FID_P] = in.prim[FID_P];
+        prim[FID_T] = in.prim[FID_T];
+        prim[FID_U] = in.prim[FID_U] - 2 * n0;
+        prim[FID_V] = in.prim[FID_V] - 2 * n1;
+        prim[FID_W] = in.prim[FID_W] - 2 * n2;
+        primitive2conservative(prim, cons_bc);
+    } else if (bc == BC_DIRICHLET) {
+        primitive2conservative(dirichlet_info, cons_bc);
+    }
+}
+
 // One cell's residual: its interfaces in the reference's processing order, `-=` on the owner side and `+=` on
 // the neighbour side (src/euler.cpp:150-247); lmax = running maximum of the interface eigenvalues (:234).
+// Only solved cells have a list, so on a boundary / wall interface the gathering cell is the fluid side
+// (src/euler.cpp:198-225): as the neighbour it evaluates the BC with the flipped normal.
 __device__ __forceinline__ void generic_cell_residual(const GenericMesh &m, const double *__restrict__ S, int64_t c,
                                                       double *acc, double &lmax)
 {
     const int64_t e0 = m.cf_ptr[c], e1 = m.cf_ptr[c + 1];
+    if (e0 == e1) return;
+    DerivedCell own;
+    load_cell(S, m.stride, c, own.cons);
+    derive_cell_generic(own);
     for (int64_t e = e0; e < e1; ++e) {
         const int32_t ent  = m.cf_ent[e];
         const int32_t f    = ent >> 1;
         const int     side = ent & 1;
-        const int32_t o    = m.f_owner[f];
-        const int32_t nb   = m.f_neigh[f];
         const int     bc   = m.f_bc[f];
         const double  A    = m.f_area[f];
         const double  nrm[3] = { m.f_normal[f], m.f_normal[m.n_ifaces + f], m.f_normal[2 * m.n_ifaces + f] };
 
-        double ownerRec[NF], neighRec[NF];
+        DerivedCell other;
         if (bc == BC_NONE) {
             // order-1 reconstruction: face state = cell mean (src/reconstruction.cpp:90-97)
-            load_cell(S, m.stride, o, ownerRec);
-            load_cell(S, m.stride, nb, neighRec);
+            load_cell(S, m.stride, side == 0 ? m.f_neigh[f] : m.f_owner[f], other.cons);
+        } else if (side == 0) {
+            bc_values_of_derived(bc, nrm, m.dirichlet_info, own, other.cons);
         } else {
-            // src/euler.cpp:198-225: the fluid side is the owner when it is solved, otherwise
-            // the neighbour; the flipped normal is used for the BC evaluation only
-            const bool ownerSolved = m.c_solved[o] != 0;
-            if (ownerSolved) {
-                load_cell(S, m.stride, o, ownerRec);
-                interface_bc_values(bc, nrm, m.dirichlet_info, ownerRec, neighRec);
-            } else {
-                const double flipped[3] = { -1. * nrm[0], -1. * nrm[1], -1. * nrm[2] };
-                load_cell(S, m.stride, nb, neighRec);
-                interface_bc_values(bc, flipped, m.dirichlet_info, neighRec, ownerRec);
-            }
+            const double flipped[3] = { -1. * nrm[0], -1. * nrm[1], -1. * nrm[2] };
+            bc_values_of_derived(bc, flipped, m.dirichlet_info, own, other.cons);
         }
+        derive_cell_generic(other);
 
-        double flux[NF], lambda;
-        eval_splitting(ownerRec, neighRec, nrm, flux, &lambda); // un-flipped normal (:232)
-        lmax = (lambda < lmax) ? lmax : lambda;                  // :234
+        // euler::evalSplitting (src/euler.cpp:42-73) with L = owner, R = neighbour and the un-flipped normal (:232)
+        double fOwn[NF], fOth[NF], unOwn, unOth;
+        fluxes_of_derived(own, nrm, fOwn, &unOwn);
+        fluxes_of_derived(other, nrm, fOth, &unOth);
+        const double lamOwn = fabs(unOwn) + own.a;
+        const double lamOth = fabs(unOth) + other.a;
+        double lam;
+        if (side == 0) lam = (lamOth < lamOwn) ? lamOwn : lamOth; // std::max(lambdaR, lambdaL), L = own
+        else           lam = (lamOwn < lamOth) ? lamOth : lamOwn; // L = other
+        lmax = (lam < lmax) ? lmax : lam;                         // :234
 
         if (side == 0) {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) acc[k] -= A * flux[k];  // :237-241
+            for (int k = 0; k < NF; ++k) {
+                const double flux = 0.5 * ((fOth[k] + fOwn[k]) - lam * (other.cons[k] - own.cons[k]));
+                acc[k] -= A * flux;                               // :237-241
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) acc[k] += A * flux[k];  // :243-247
+            for (int k = 0; k < NF; ++k) {
+                const double flux = 0.5 * ((fOwn[k] + fOth[k]) - lam * (own.cons[k] - other.cons[k]));
+                acc[k] += A * flux;                               // :243-247
+            }
         }
     }
 }

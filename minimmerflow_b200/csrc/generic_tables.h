@@ -29,6 +29,10 @@ struct GenericTables {
     std::vector<uint8_t> solved, update; // update = solved AND internal (the cells the RK loops touch)
     std::vector<int64_t> ptr;           // [n_cells + 1]
     std::vector<int32_t> ent;           // (interface raw id << 1) | side, side 0 = owner, 1 = neigh
+    // a boundary condition on an interface between two SOLVED cells: the reference never builds one (BC_WALL sits
+    // between a solved and an unsolved cell, src/main.cpp:251-277) but evaluates it from the owner's state for both
+    // sides (src/euler.cpp:198-225); the fused stage kernel assumes the gathering cell is the fluid side
+    bool bc_between_solved = false;
 };
 
 // returns MMF_OK or MMF_ERR_INVALID with a message in err
@@ -83,6 +87,7 @@ inline int build_generic_tables(const mmf_mesh_desc *d, GenericTables &t, std::s
         if (f < 0 || f >= nf) return bad("mmf_create: interface_order[%lld] out of range", (long long) q, 0);
         bool oS, nS;
         if (!processed(f, oS, nS)) continue;
+        if (oS && nS && t.bc[f] != MMF_BC_NONE) t.bc_between_solved = true;
         if (oS) t.ptr[t.owner[f] + 1]++;
         if (nS) t.ptr[t.neigh[f] + 1]++;
     }

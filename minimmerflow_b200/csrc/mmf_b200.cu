@@ -111,7 +111,8 @@ static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
         if ((rc = dev_alloc(ctx, &ctx->fields[i], (size_t) NF * g.stride))) return rc;
         MMF_CUDA(ctx, cudaMemset(ctx->fields[i], 0, sizeof(double) * NF * g.stride));
     }
-    ctx->generic_fused = getenv("MMF_GENERIC_FUSED") && atoi(getenv("MMF_GENERIC_FUSED")) != 0;
+    // (not for a description with a boundary condition between two solved cells, see generic_tables.h)
+    ctx->generic_fused = getenv("MMF_GENERIC_FUSED") && atoi(getenv("MMF_GENERIC_FUSED")) != 0 && !t.bc_between_solved;
     if (ctx->generic_fused) {
         if ((rc = dev_alloc(ctx, &ctx->w_alt, (size_t) NF * g.stride))) return rc;
         MMF_CUDA(ctx, cudaMemset(ctx->w_alt, 0, sizeof(double) * NF * g.stride));

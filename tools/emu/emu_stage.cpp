@@ -450,6 +450,7 @@ int emu_generic_run(const mmf_mesh_desc *d, int fused, double *U, double *W, dou
     GenericTables tb;
     std::string msg;
     if (build_generic_tables(d, tb, msg)) return -1;
+    if (tb.bc_between_solved) fused = 0; // as create_generic decides
     GenericMesh m{};
     m.n_cells = tb.n_cells; m.n_ifaces = tb.n_ifaces; m.stride = tb.stride;
     m.cf_ptr = tb.ptr.data(); m.cf_ent = tb.ent.data();
