@@ -78,7 +78,7 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ S, int64_t 
 // side of every interface in its list, so the fused stage kernel (generic_stage_kernel) derives it once --
 // primitives (src/utils.cpp:48-63), sound speed, |v|^2 and total energy as src/euler.cpp:52-58, 83-92 form them
 // -- and per interface derives the other side only.  Same inputs, same operations, same order => the same bits
-// (checked against the oracle on the emulator, tests/test_emu_generic.py); about a third fewer FP64
+// (checked bit for bit on the CPU by tests/test_emu_generic.py); about a third fewer FP64
 // instructions per cell.  generic_rhs_kernel keeps the reference-shaped text: its SASS is the one the GPU parity
 // runs validated.
 struct DerivedCell {
@@ -320,6 +320,22 @@ __global__ void __launch_bounds__(128) generic_stage_kernel(GenericMesh m, const
                 Out[i] = Sin[i];
             }
         }
+    }
+    block_max_to_global(lmax, max_eig);
+}
+
+// The stage-1 residual of the fused sequence: generic_rhs_kernel's result from generic_cell_residual (the
+// gathering cell derived once).  Stage 1 itself stays two kernels, its dt comes out of this one's maximum.
+__global__ void __launch_bounds__(128) generic_rhs_derived_kernel(GenericMesh m, const double *__restrict__ S,
+                                                                  double *__restrict__ RHS, double *__restrict__ max_eig)
+{
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double lmax = 0.0;
+    if (c < m.n_cells) {
+        double acc[NF] = { 0., 0., 0., 0., 0. };
+        generic_cell_residual(m, S, c, acc, lmax);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) RHS[k * m.stride + c] = acc[k];
     }
     block_max_to_global(lmax, max_eig);
 }

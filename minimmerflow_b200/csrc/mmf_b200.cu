@@ -334,15 +334,21 @@ extern "C" int mmf_compute_polynomials(mmf_ctx *ctx, int field)
 }
 
 // residual of `field` into RHS, face-max eigenvalue into ctl->max_eig[slot]; no synchronisation
-static int rhs_enqueue(mmf_ctx *ctx, int field, int slot)
+// derived: the fused sequence's variant of the generic residual kernel (MMF_GENERIC_FUSED=1, step_enqueue only)
+static int rhs_enqueue(mmf_ctx *ctx, int field, int slot, bool derived = false)
 {
     double *d_max = &ctx->d_ctl->max_eig[slot];
     MMF_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(double), ctx->stream));
     if (ctx->path == MMF_PATH_UNIFORM) return uniform_rhs(ctx, field, d_max);
     {
         ScopedLaunchTimer timer(ctx, 0);
-        generic_rhs_kernel<<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
-            ctx->gm, ctx->fields[field], ctx->fields[MMF_FIELD_RHS], d_max);
+        if (derived) {
+            generic_rhs_derived_kernel<<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
+                ctx->gm, ctx->fields[field], ctx->fields[MMF_FIELD_RHS], d_max);
+        } else {
+            generic_rhs_kernel<<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
+                ctx->gm, ctx->fields[field], ctx->fields[MMF_FIELD_RHS], d_max);
+        }
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -442,7 +448,7 @@ static int step_enqueue(mmf_ctx *ctx)
     int rc;
     if (ctx->path == MMF_PATH_UNIFORM) return uniform_step(ctx);
     // unfused reference-shaped sequence (src/main.cpp:383-506)
-    if ((rc = rhs_enqueue(ctx, MMF_FIELD_U, 0))) return rc;
+    if ((rc = rhs_enqueue(ctx, MMF_FIELD_U, 0, ctx->generic_fused))) return rc;
     if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0], 1))) return rc;
     choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_ctl);
     MMF_LAUNCH_CHECK(ctx);
