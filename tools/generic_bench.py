@@ -16,9 +16,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import minimmerflow_b200 as mmf  # noqa: E402
-import oracle_lib  # noqa: E402  (mesh generator only: the oracle computes nothing here)
+from minimmerflow_b200.meshes import box_mesh, vortex_state, with_bodies  # noqa: E402
 
 
 def main():
@@ -28,15 +27,17 @@ def main():
     ap.add_argument("--problem", default="vortex_xy")
     ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain; the fused path then needs MMF_UNIFORM_BODIES=1")
     args = ap.parse_args()
-    orc = oracle_lib.load()
-    boxes = None
+    if args.problem != "vortex_xy":
+        raise SystemExit("generic_bench.py builds the isentropic vortex (vortex_xy) only")
+    # the benchmark domain (src/problem.cpp:70-149: origin -5, length 10), free-flow borders, lexicographic numbering
+    origin, length = (-5.0, -5.0, -5.0), 10.0
+    n = args.size
+    m = box_mesh(n, n, n, length / n, 0, origin=origin)
     if args.bodies:
         os.environ.setdefault("MMF_UNIFORM_BODIES", "1")   # 1 = form b, 2 = form c
-        _, origin, length = orc.domain(args.problem, 3)
         lo = lambda f: [origin[e] + f[e] * length for e in range(3)]
-        boxes = [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))]
-    m = orc.problem_mesh(args.problem, 3, args.size, boxes=boxes)
-    U = orc.init_state(m)
+        m = with_bodies(m, [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))])
+    U = vortex_state(m)
     cells = m["volume"].shape[0]
     out = {}
     for name, flags in (("uniform", 0), ("generic", mmf.FLAG_FORCE_GENERIC)):
