@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call for the stage-kernel forms that were developed on the CPU emulator (tools/emu) and have
 # never run on a GPU: parity first, then the sweep that decides whether they become the default.
-#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/gpu_first_call.sh'
 # (every step has its own, shorter timeout: a form that hangs on real hardware costs its own group only)
 # Everything lands in gpurun_out/.
 set -u
@@ -24,7 +24,7 @@ MMF_UNIFORM_BODIES=1 MMF_DEVICE_PRIMITIVES=1 timeout 600 python -m pytest tests/
 echo "drop-in exit code: $?" | tee -a gpurun_out/experimental_dropin.log
 tail -3 gpurun_out/experimental_dropin.log
 # 2. sweep at the benchmark size: per-stage kernel times, bitwise equality with the default mix
-timeout 600 python tools/stage_sweep.py --size 256 --steps 6 > gpurun_out/stage_sweep_256.jsonl 2> gpurun_out/stage_sweep_256.err
+timeout 1200 python tools/stage_sweep.py --size 256 --steps 6 > gpurun_out/stage_sweep_256.jsonl 2> gpurun_out/stage_sweep_256.err
 cat gpurun_out/stage_sweep_256.jsonl
 # 3. z-chunk sensitivity of the two most promising mixes
 for lz in 26 32 43 52 64; do

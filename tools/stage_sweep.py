@@ -25,40 +25,86 @@ def vortex(n):
     return np.broadcast_to(plane[None], (n, n, n, 5)).reshape(-1, 5).copy(), h
 
 
+def run_one(var, size, steps):
+    """One variant in THIS process: per-stage kernel times, whole-step time and a checksum of the final state."""
+    import hashlib
+    U, h = vortex(size)
+    cells = size ** 3
+    cfg, lz = var.split("@") if "@" in var else (var, "0")   # e.g. p16:p16:r12:r12@43
+    os.environ["MMF_STAGE_CFG"] = cfg
+    if int(lz) > 0:
+        os.environ["MMF_STAGE_LZ"] = lz
+    else:
+        os.environ.pop("MMF_STAGE_LZ", None)
+    with mmf.EulerSolver.uniform((size,) * 3, h, [0] * 6, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC) as s:
+        s.set_state(mmf.FIELD_U, U)
+        s.run(0.45, h, 0.0, 1e30, max_steps=3)
+        s.timer_start()
+        s.run(0.45, h, 0.0, 1e30, max_steps=steps)
+        ms = s.timer_stop()
+        s.profile_begin()
+        s.run(0.45, h, 0.0, 1e30, max_steps=steps)
+        kms, kn = s.profile_end()
+        out = s.get_state(mmf.FIELD_U)
+    st = [kms[i] / max(kn[i], 1) for i in (1, 2, 3)]
+    return {"variant": var, "ms_per_step": ms / steps, "stage_ms": st,
+            "cell_updates_per_s": cells * 3 * steps / (ms * 1e-3),
+            "stage_GBps": [b * cells / (t * 1e-3) / 1e9 for b, t in zip((80, 120, 120), st)],
+            "state_sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()}
+
+
+def summarise(rows):
+    """What the sweep says: the fastest whole step, and per stage the fastest kernel among the bit-identical variants
+    (candidate_mix = stage 0 : 1 : 2 : 3 shapes for MMF_STAGE_CFG; stage 0, the RHS-only launch, follows stage 1)."""
+    good = [r for r in rows if r.get("bitwise_equal_to_first")]
+    if not good:
+        return None
+
+    def stage_shape(r, st):   # the shape a variant runs stage st (1..3) with; one entry = all stages
+        parts = r["variant"].split("@")[0].split(":")
+        return parts[st] if len(parts) > st else parts[-1]
+    best_step = min(good, key=lambda r: r["ms_per_step"])
+    per_stage = [min(good, key=lambda r, i=i: r["stage_ms"][i]) for i in range(3)]
+    mix = [stage_shape(per_stage[0], 1)] + [stage_shape(per_stage[i], i + 1) for i in range(3)]
+    return {"summary": True, "fastest_step": best_step["variant"], "fastest_step_ms": best_step["ms_per_step"],
+            "fastest_per_stage": [{"stage": i + 1, "variant": per_stage[i]["variant"], "shape": stage_shape(per_stage[i], i + 1),
+                                   "ms": per_stage[i]["stage_ms"][i]} for i in range(3)],
+            "candidate_mix": ":".join(mix),
+            "not_bit_identical": [r["variant"] for r in rows if not r.get("bitwise_equal_to_first")]}
+
+
 def main():
+    import subprocess
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--variants", default="p16:p16:r12:r12,p16:p16:d12:d12,p16:p16:h12:h12,p16:h16:h12:h12,p16:p16:w8:w8,p16:w8:w8:w8,w8,h12,h16,d12,d16,p12,r12,p16,r16,312")
+    ap.add_argument("--variant-timeout", type=float, default=90.0,
+                    help="seconds per variant: every variant runs in its own process, so a kernel form that hangs on real "
+                         "hardware costs its own slot only")
+    ap.add_argument("--one", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    U, h = vortex(args.size)
-    cells = args.size ** 3
-    ref = None
+    if args.one is not None:
+        print(json.dumps(run_one(args.one, args.size, args.steps)), flush=True)
+        return
+    rows, ref = [], None
     for var in args.variants.split(","):
-        cfg, lz = var.split("@") if "@" in var else (var, "0")   # e.g. p16:p16:r12:r12@43
-        os.environ["MMF_STAGE_CFG"] = cfg
-        if int(lz) > 0:
-            os.environ["MMF_STAGE_LZ"] = lz
-        else:
-            os.environ.pop("MMF_STAGE_LZ", None)
-        with mmf.EulerSolver.uniform((args.size,) * 3, h, [0] * 6, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC) as s:
-            s.set_state(mmf.FIELD_U, U)
-            s.run(0.45, h, 0.0, 1e30, max_steps=3)
-            s.timer_start()
-            s.run(0.45, h, 0.0, 1e30, max_steps=args.steps)
-            ms = s.timer_stop()
-            s.profile_begin()
-            s.run(0.45, h, 0.0, 1e30, max_steps=args.steps)
-            kms, kn = s.profile_end()
-            out = s.get_state(mmf.FIELD_U)
-        if ref is None:
-            ref = out
-        same = bool(np.array_equal(out, ref))
-        st = [kms[i] / max(kn[i], 1) for i in (1, 2, 3)]
-        print(json.dumps({"variant": var, "ms_per_step": ms / args.steps, "stage_ms": st,
-                          "cell_updates_per_s": cells * 3 * args.steps / (ms * 1e-3),
-                          "stage_GBps": [b * cells / (t * 1e-3) / 1e9 for b, t in zip((80, 120, 120), st)],
-                          "bitwise_equal_to_first": same}), flush=True)
+        cmd = [sys.executable, os.path.abspath(__file__), "--size", str(args.size), "--steps", str(args.steps), "--one", var]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=args.variant_timeout)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            row = json.loads(lines[-1]) if r.returncode == 0 and lines else {"variant": var, "error": (r.stderr or "no output")[-400:]}
+        except subprocess.TimeoutExpired:
+            row = {"variant": var, "error": f"timeout after {args.variant_timeout:.0f} s"}
+        if "error" not in row:
+            if ref is None:
+                ref = row["state_sha256"]
+            row["bitwise_equal_to_first"] = row["state_sha256"] == ref
+            rows.append(row)
+        print(json.dumps(row), flush=True)
+    summary = summarise(rows)
+    if summary:
+        print(json.dumps(summary), flush=True)
 
 
 if __name__ == "__main__":
