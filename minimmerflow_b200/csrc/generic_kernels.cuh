@@ -374,13 +374,19 @@ __global__ void set_dt_kernel(StepControl *ctl, double dt)
 }
 
 // src/main.cpp:505-506; check_eig: the uniform path compares the eigenvalue that chose dt with the
-// face maximum the fused stage-1 kernel re-derived
+// face maximum the fused stage-1 kernel re-derived.
+// A step enqueued at t >= tMax switched itself off: U is unchanged, so the eigenvalue this step started from
+// (max_eig[0]) is still the one of U and stays the next step's candidate -- the stage kernels returned early, and
+// whatever the eigenvalue passes behind stage 3 left in eig_next comes from stale tile estimates without the ghost
+// cells' own values.
 __global__ void advance_time_kernel(StepControl *ctl, int check_eig)
 {
     if (ctl->active != 0.0) {
         ctl->t += ctl->dt;
         ctl->steps += 1.0;
         if (check_eig && ctl->max_eig_chk != ctl->max_eig[0]) ctl->mismatches += 1.0;
+    } else if (check_eig) {
+        ctl->eig_next = ctl->max_eig[0];
     }
 }
 

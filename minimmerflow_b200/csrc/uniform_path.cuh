@@ -172,6 +172,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         const StageShape &s3 = u->shape[3];
         u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.rows() - 1) / s3.rows()) * ((g.nz + s3.lz - 1) / s3.lz);
         if ((rc = dev_alloc(ctx, &u->cta_est, (size_t) u->n_tiles3))) return rc;
+        MMF_CUDA(ctx, cudaMemsetAsync(u->cta_est, 0, sizeof(float) * u->n_tiles3, ctx->stream));
         if ((rc = dev_alloc(ctx, &u->eig_cand, (size_t) u->n_tiles3 + 1))) return rc;
     }
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -819,8 +819,8 @@ static void *worker_main(void *arg)
     return NULL;
 }
 
-double orc_bench_threads(int problem, int dim_in, int level, int n_warmup, int n_steps, int n_threads,
-                         double cfl, uint64_t *state_hash)
+static double run_threads(int problem, int dim_in, int level, int n_warmup, int n_steps, int n_threads,
+                          double cfl, uint64_t *state_hash, double *U0_out, double *U_out)
 {
     int dim;
     double origin[3], length;
@@ -835,6 +835,7 @@ double orc_bench_threads(int problem, int dim_in, int level, int n_warmup, int n
     double *W   = calloc(NF * m.n_cells, sizeof(double));
     double *RHS = calloc(NF * m.n_cells, sizeof(double));
     orc_init_state(problem, dim, m.n_cells, m.ccentroid, 0.0, U);
+    if (U0_out) memcpy(U0_out, U, sizeof(double) * NF * m.n_cells);
 
     if (n_threads < 1) n_threads = 1;
     if (n_threads > m.n_cells) n_threads = (int) m.n_cells;
@@ -884,6 +885,7 @@ double orc_bench_threads(int problem, int dim_in, int level, int n_warmup, int n
         }
         *state_hash = hsh;
     }
+    if (U_out) memcpy(U_out, U, sizeof(double) * NF * m.n_cells);
 
     for (int t = 0; t < n_threads; ++t) free(ws[t].iface);
     pthread_barrier_destroy(&bar);
@@ -891,4 +893,19 @@ double orc_bench_threads(int problem, int dim_in, int level, int n_warmup, int n
     free(U); free(W); free(RHS);
     mesh_free(&m);
     return secs;
+}
+
+double orc_bench_threads(int problem, int dim_in, int level, int n_warmup, int n_steps, int n_threads,
+                         double cfl, uint64_t *state_hash)
+{
+    return run_threads(problem, dim_in, level, n_warmup, n_steps, n_threads, cfl, state_hash, NULL, NULL);
+}
+
+/* The same threaded loop as a CHECKER for large meshes: n_steps RK3 steps (no tMax clamp, like
+ * main.cpp:398-402 while t + dt stays below tMax) from the problem's initial state; returns the initial and the
+ * final conservative fields in Morton cell order.  Bitwise equal to the serial loop (see above). */
+void orc_run_threads(int problem, int dim_in, int level, int n_steps, int n_threads, double cfl,
+                     double *U0_out, double *U_out)
+{
+    run_threads(problem, dim_in, level, 0, n_steps, n_threads, cfl, NULL, U0_out, U_out);
 }

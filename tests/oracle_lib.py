@@ -57,6 +57,8 @@ class Oracle:
         L.orc_bench_threads.restype = C.c_double
         L.orc_bench_threads.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.POINTER(C.c_uint64)]
+        L.orc_run_threads.restype = None
+        L.orc_run_threads.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _D, _D]
         L.orc_conservative2primitive.argtypes = [_D, _D]
         L.orc_primitive2conservative.argtypes = [_D, _D]
         L.orc_eval_splitting.argtypes = [_D, _D, _D, _D, _D]
@@ -161,6 +163,28 @@ class Oracle:
         h = C.c_uint64(0)
         secs = self.lib.orc_bench_threads(PROBLEMS[problem], dim, level, n_warmup, n_steps, n_threads, cfl, C.byref(h))
         return secs, h.value
+
+
+    def run_threads(self, problem, dim, level, n_steps, n_threads=0, cfl=0.45):
+        """n_steps RK3 steps (no tMax clamp) on 2^level cells per side with the threaded loop (bitwise the serial
+        one); returns (U0, U) in Morton cell order.  The checker for meshes the serial loop is too slow for."""
+        n_threads = n_threads or (os.cpu_count() or 1)
+        nc = (1 << level) ** dim
+        U0, U = np.empty((nc, 5)), np.empty((nc, 5))
+        self.lib.orc_run_threads(PROBLEMS[problem], dim, level, n_steps, n_threads, cfl, _p(U0, _D), _p(U, _D))
+        return U0, U
+
+
+def morton_to_lexicographic(n, dim=3):
+    """perm with lexi_state[perm] = morton_state ... i.e. perm[m] = lexicographic index of the cell whose Morton id is m
+    (x = lowest bit; n a power of two)."""
+    m = np.arange(n ** dim, dtype=np.int64)
+    bits = int(np.log2(n))
+    coords = [np.zeros_like(m) for _ in range(3)]
+    for b in range(bits):
+        for a in range(dim):
+            coords[a] |= ((m >> (dim * b + a)) & 1) << b
+    return (coords[2] * n + coords[1]) * n + coords[0]
 
 
 _oracle = None

@@ -94,6 +94,20 @@ def test_threaded_baseline_is_bitwise_serial(oracle):
     assert h1 == h3 == h8
 
 
+def test_threaded_checker_equals_serial_run(oracle):
+    """orc_run_threads (the checker of the 128^3 / 256^3 GPU parity tests) == the serial main.cpp loop, bit for
+    bit, on any thread count; its initial state is the problem's; the Morton -> lexicographic permutation is the
+    mesh's own cell_ijk."""
+    import oracle_lib
+    ref = oracle.run("vortex_xy", 3, 32, t_end=1e30, max_steps=4, want_state=True)
+    m = oracle.problem_mesh("vortex_xy", 3, 32)
+    for threads in (1, 3, 8):
+        U0, U = oracle.run_threads("vortex_xy", 3, 5, 4, threads)
+        assert bits_equal(U, ref["U"]) and bits_equal(U0, oracle.init_state(m))
+    ijk = m["cell_ijk"].astype(np.int64)
+    assert np.array_equal(oracle_lib.morton_to_lexicographic(32), (ijk[:, 2] * 32 + ijk[:, 1]) * 32 + ijk[:, 0])
+
+
 def test_body_boxes_make_wall_faces(oracle):
     boxes = np.array([[3.0, 3.0, 3.0, 5.0, 5.0, 5.0]])
     m = oracle.problem_mesh("radsod", 3, 16, boxes=boxes)

@@ -279,6 +279,30 @@ def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle, monkeypatch):
         assert s.info()["path"] == mmf.PATH_GENERIC
 
 
+@pytest.mark.parametrize("n,steps", [(64, 10), (128, 10), (256, 3)])
+def test_bench_configuration_bit_exact(mmf, oracle, n, steps):
+    """The configuration bench.py times -- compact descriptor, LEXICOGRAPHIC cell numbering with the MORTON
+    interface order, free-flow load clamps, default kernel mix -- against the oracle at 64^3 / 128^3 (10 steps,
+    SURVEY 8d) and at the full benchmark size 256^3 (3 steps, the threaded loop of the oracle, which is bitwise the
+    serial one: tests/test_oracle_units.py).  The oracle's cells are Morton numbered: the per-cell values do not
+    depend on the CELL numbering (the accumulation order follows the interface numbering), so they are compared
+    cell by cell after the permutation.  Bitwise."""
+    level = n.bit_length() - 1
+    h = 10.0 / n
+    U0m, Urefm = oracle.run_threads("vortex_xy", 3, level, steps)
+    perm = oracle_lib.morton_to_lexicographic(n)
+    U0 = np.empty_like(U0m); U0[perm] = U0m
+    with mmf.EulerSolver.uniform((n, n, n), h, [0] * 6, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC,
+                                 interface_numbering=mmf.NUMBERING_MORTON) as s:
+        info = s.info()
+        assert info["path"] == mmf.PATH_UNIFORM and info["order_exact"] == 1
+        s.set_state(mmf.FIELD_U, U0)
+        t, done = s.run(0.45, h, 0.0, 1e30, max_steps=steps)
+        assert done == steps
+        got = s.get_state(mmf.FIELD_U)
+    assert bits_equal(got[perm], Urefm), max_rel_diff(got[perm], Urefm)
+
+
 def test_large_mesh_properties(mmf):
     """Full benchmark size (256^3): properties that need no oracle.
     (1) a uniform free-stream state is a fixed point of the scheme (every interface flux cancels);
@@ -348,6 +372,60 @@ def test_next_step_eigenvalue_from_stage3_estimates(mmf, oracle, problem):
         tb, nb = s.run(0.45, m["h"], 0.0, 1e30, max_steps=12)
         assert nb == 12 and tb == t
         assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+
+
+@pytest.mark.parametrize("kind", ["radsod", "dirichlet"])
+def test_run_to_tmax_then_continue(mmf, oracle, kind):
+    """mmf_run enqueues steps in batches; those past tMax switch themselves off on the device.  A second run on the
+    same handle (a later tMax) must start from the right max eigenvalue -- including the boundary ghosts' own
+    (reflecting images, a Dirichlet inflow that holds the maximum) -- and a run called at t >= tMax must change
+    nothing.  dt sequence and state bitwise against the oracle stepping with the same two end times."""
+    if kind == "radsod":
+        m = oracle.problem_mesh("radsod", 3, 16)
+        U = oracle.init_state(m)
+        make = lambda: mmf.EulerSolver.from_mesh(m)
+    else:
+        m = lexicographic_box_mesh(14, 9, 5, 0.25, 1)
+        m["problem"] = "ffstep"
+        border = m["neigh"] < 0
+        m["bc"][border & (m["normal"][:, 0] < 0)] = 3       # -x Dirichlet (u = 3: it holds the largest eigenvalue)
+        m["bc"][border & (m["normal"][:, 0] > 0)] = 0
+        rng = np.random.default_rng(5)
+        nc = m["volume"].shape[0]
+        rho = rng.uniform(0.9, 1.1, nc); vel = rng.uniform(-0.1, 0.1, (nc, 3)); p = rng.uniform(0.9, 1.1, nc)
+        U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
+        make = lambda: mmf.EulerSolver.from_mesh(m, problem_type=7, dirichlet_info=[1.0, 3.0, 0.0, 0.0, 1.0 / 1.4])
+    h = float(m["size"].min())
+    # oracle: main.cpp's loop with tMax = T1, then continued with tMax = T2
+    dt0, _ = oracle.step(m, 0.45, 0.0, 1e30, U.copy(), np.zeros_like(U), np.zeros_like(U))
+    T1, T2 = 3.4 * dt0, 7.7 * dt0
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    t, n1, n2 = 0.0, 0, 0
+    while t < T1:
+        t += oracle.step(m, 0.45, t, T1, Uo, Wo, Ro)[0]; n1 += 1
+    U1 = Uo.copy()
+    while t < T2:
+        t += oracle.step(m, 0.45, t, T2, Uo, Wo, Ro)[0]; n2 += 1
+    with make() as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+        s.set_state(mmf.FIELD_U, U)
+        assert s.run(0.45, h, T1, T1) == (T1, 0)             # first call at t >= tMax: nothing happens
+        assert bits_equal(s.get_state(mmf.FIELD_U), U)
+        ta, na = s.run(0.45, h, 0.0, T1)
+        assert (ta, na) == (T1, n1) and bits_equal(s.get_state(mmf.FIELD_U), U1)
+        assert s.run(0.45, h, ta, T1) == (T1, 0)
+        tb, nb = s.run(0.45, h, ta, T2)
+        assert (tb, nb) == (T2, n2)
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
+        # and step by step through mmf_step, with a step at t >= tMax in between
+        s.set_state(mmf.FIELD_U, U)
+        t = 0.0
+        while t < T1:
+            t += s.step(0.45, h, t, T1)[0]
+        assert s.step(0.45, h, t, T1)[0] == 0.0
+        while t < T2:
+            t += s.step(0.45, h, t, T2)[0]
+        assert t == T2 and bits_equal(s.get_state(mmf.FIELD_U), Uo)
 
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 3), (31, 11, 1), (30, 10, 4), (61, 21, 5)])
