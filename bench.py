@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--cpu-level", type=int, default=0, help="oracle-port mesh level for the CPU legs (0 = 7)")
     ap.add_argument("--cpu-size", type=int, default=0, help="cells per side for the compiled-reference CPU leg (0 = 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check that precedes the timed region")
+    ap.add_argument("--repeats", type=int, default=5,
+                    help="the timed region (exactly --steps steps between barriers) is run this many times; the line reports "
+                         "the MEDIAN repeat and lists all of them (SURVEY 8d)")
     ap.add_argument("--nccl-halo", action="store_true", help="exchange halos with NCCL send/recv instead of direct peer stores")
     return ap.parse_args()
 
@@ -109,10 +113,8 @@ class ClockSampler(threading.Thread):
 
 def stage_kernel_label():
     """Name of the kernel that runs stages 2 and 3 (the dominant one), from the same knob the library reads."""
-    names = {"p": "uniform_stage_kernel_v5", "r": "uniform_stage_kernel_v5r", "d": "uniform_stage_kernel_v6",
-             "h": "uniform_stage_kernel_v6 (merged halo warp)", "w": "uniform_stage_kernel_v7 (two y rows per warp)",
-             "3": "uniform_stage_kernel_v3"}
-    shapes = ["p16", "p16", "r12", "r12"]                      # library defaults (uniform_path.cuh)
+    names = {"r": "uniform_stage_kernel_v5r", "m": "uniform_stage_kernel_v5m (bulk tensor stores)"}
+    shapes = ["r12"] * 4                                       # library defaults (uniform_path.cuh)
     cfg = [c for c in os.environ.get("MMF_STAGE_CFG", "").split(":") if c]
     if len(cfg) == 1:
         shapes = cfg * 4
@@ -257,6 +259,91 @@ def workload_config(dims, gdims, grid):
             "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
 
 
+# ---- parity inside the bench run (the oracle as the checker, never as the thing measured) ----------
+PARITY_STEPS = 3
+
+
+def ulp_distance(a, b):
+    """Largest distance in units in the last place between two float64 arrays (+0 == -0)."""
+    a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+    b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+    bad = a != b
+    if not bad.any():
+        return 0, 0
+    ia, ib = a[bad].view(np.int64), b[bad].view(np.int64)
+    # map the sign-magnitude bit patterns onto a monotone integer line
+    ia = np.where(ia < 0, np.int64(-2 ** 63) - ia, ia)
+    ib = np.where(ib < 0, np.int64(-2 ** 63) - ib, ib)
+    with np.errstate(over="ignore"):
+        d = np.abs(ia - ib)                                  # int64; wraps only for values of opposite huge magnitude
+    far = (d < 0) | (np.sign(ia) * np.sign(ib) < 0) & (np.abs(ia.astype(np.float64) - ib.astype(np.float64)) > 2.0 ** 62)
+    d[far] = np.iinfo(np.int64).max
+    return int(d.max()), int(bad.sum())
+
+
+def parity_check(args, make_solver, dist, rank, world, grid, coords):
+    """Before anything is timed: PARITY_STEPS RK3 steps of the benchmark problem on a size^3 cube cut by the SAME
+    process grid, kernels, numbering conventions and halo exchange as the timed run, every rank's box compared
+    bit for bit with the CPU oracle (oracle/mmf_oracle.c, threaded loop; rank 0 runs it and broadcasts).  At N = 1
+    this is the timed configuration itself.  Exits non-zero on any difference."""
+    S = args.size
+    if args.no_parity or S & (S - 1) or any(S % g for g in grid):
+        return {"checked": False, "why": "disabled (--no-parity)" if args.no_parity else
+                f"the oracle's octree mesh needs a power-of-two cube divisible by the process grid, size is {S}"}
+    import minimmerflow_b200 as mmf
+    t0 = time.perf_counter()
+    level = S.bit_length() - 1
+    n = S ** 3
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        orc = oracle_lib.load()
+        U0m, Urm = orc.run_threads("vortex_xy", 3, level, PARITY_STEPS)
+        perm = oracle_lib.morton_to_lexicographic(S)
+        both = np.empty((2, n, 5))
+        both[0][perm] = U0m
+        both[1][perm] = Urm
+        del U0m, Urm, perm
+    else:
+        both = np.empty((2, n, 5))
+    if world > 1:
+        import torch
+        for q in range(2):   # one array at a time: 671 MB each at 256^3
+            tt = torch.from_numpy(both[q]).cuda()
+            dist.broadcast(tt, src=0)
+            both[q] = tt.cpu().numpy()
+            del tt
+        torch.cuda.empty_cache()
+    box = (S // grid[0], S // grid[1], S // grid[2])
+    off = (coords[0] * box[0], coords[1] * box[1], coords[2] * box[2])
+    sl = (slice(off[2], off[2] + box[2]), slice(off[1], off[1] + box[1]), slice(off[0], off[0] + box[0]))
+    G = both.reshape(2, S, S, S, 5)
+    mine0 = np.ascontiguousarray(G[0][sl]).reshape(-1, 5)
+    mine1 = np.ascontiguousarray(G[1][sl]).reshape(-1, 5)
+    del both, G
+    h = 10.0 / S
+    with make_solver(box, (S, S, S), off, h) as sol:
+        sol.set_state(mmf.FIELD_U, mine0)
+        _, done = sol.run(0.45, h, 0.0, 1.0e30, max_steps=PARITY_STEPS)
+        got = sol.get_state(mmf.FIELD_U)
+    ulp, n_bad = ulp_distance(got, mine1)
+    if world > 1:
+        import torch
+        tt = torch.tensor([float(ulp), float(n_bad)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ulp, n_bad = int(tt[0]), int(tt[1])
+    out = {"checked": True, "max_ulp": ulp, "values_differing": n_bad, "steps": PARITY_STEPS,
+           "what": f"{S}^3 vortex_xy cube cut into {grid[0]}x{grid[1]}x{grid[2]} boxes of {box[0]}x{box[1]}x{box[2]}, "
+                   f"{PARITY_STEPS} RK3 steps, every rank's box against the CPU oracle (threaded loop, bitwise the serial "
+                   f"one), same kernels / numbering / halo exchange as the timed run",
+           "seconds": round(time.perf_counter() - t0, 1)}
+    if ulp != 0 or done != PARITY_STEPS:
+        if rank == 0:
+            print(json.dumps({"parity": out, "error": "GPU result differs from the oracle"}), flush=True)
+        sys.exit(3)
+    return out
+
+
 # ---- our arm --------------------------------------------------------------------------------------
 def run_ours(args):
     import ctypes as C
@@ -284,6 +371,33 @@ def run_ours(args):
     cells_total = cells_local * world
 
     lib = mmf.load_library()
+
+    def make_solver(box, gbox, off, hh):
+        """One rank's handle for the box `box` at `off` of the global lattice `gbox`, the benchmark's numbering
+        conventions, halo exchange set up for the process grid."""
+        sol = mmf.EulerSolver.uniform(box, hh, [mmf.BC_FREE_FLOW] * 6, device=local_rank,
+                                      cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC, interface_numbering=mmf.NUMBERING_MORTON,
+                                      global_dims=gbox, box_offset=off)
+        if world > 1:
+            uid = [mmf.EulerSolver.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            sol.comm_init(rank, world, uid[0])
+            def nb(dx, dy, dz):
+                x, y, z = cx + dx, cy + dy, cz + dz
+                if not (0 <= x < px and 0 <= y < py and 0 <= z < pz):
+                    return -1
+                return (z * py + y) * px + x
+            sol.comm_set_box_neighbours([nb(-1, 0, 0), nb(1, 0, 0), nb(0, -1, 0), nb(0, 1, 0), nb(0, 0, -1), nb(0, 0, 1)])
+            if not args.nccl_halo:
+                # halo exchange by direct peer stores over NVLink: gather every rank's CUDA IPC handles
+                blobs = [None] * world
+                dist.all_gather_object(blobs, sol.comm_ipc_export())
+                sol.comm_ipc_import(blobs)
+        return sol
+
+    # parity first: the numbers below are only worth reading next to a green check of the same code path
+    parity = parity_check(args, make_solver, dist, rank, world, (px, py, pz), (cx, cy, cz))
+
     # pinned host AoS buffer (the reference's storage layout), filled plane by plane
     nbytes = cells_local * 5 * 8
     hptr = C.c_void_p()
@@ -294,25 +408,7 @@ def run_ours(args):
     for k in range(dims[2]):
         host[k] = flat_plane
 
-    s = mmf.EulerSolver.uniform(dims, h, [mmf.BC_FREE_FLOW] * 6, device=local_rank,
-                                cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC, interface_numbering=mmf.NUMBERING_MORTON,
-                                global_dims=gdims, box_offset=offset)
-    if world > 1:
-        import torch
-        uid = [mmf.EulerSolver.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        s.comm_init(rank, world, uid[0])
-        def nb(dx, dy, dz):
-            x, y, z = cx + dx, cy + dy, cz + dz
-            if not (0 <= x < px and 0 <= y < py and 0 <= z < pz):
-                return -1
-            return (z * py + y) * px + x
-        s.comm_set_box_neighbours([nb(-1, 0, 0), nb(1, 0, 0), nb(0, -1, 0), nb(0, 1, 0), nb(0, 0, -1), nb(0, 0, 1)])
-        if not args.nccl_halo:
-            # halo exchange by direct peer stores over NVLink: gather every rank's CUDA IPC handles
-            blobs = [None] * world
-            dist.all_gather_object(blobs, s.comm_ipc_export())
-            s.comm_ipc_import(blobs)
+    s = make_solver(dims, gdims, offset, h)
 
     def barrier():
         if dist is not None:
@@ -327,14 +423,23 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = s.info()["kernel_launches"]
-    barrier()
-    s.timer_start()
-    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)                  # exactly K timed steps
-    ms = s.timer_stop()
-    barrier()
-    launches = s.info()["kernel_launches"] - launches0
+    repeats_ms, launches = [], 0
+    for _ in range(max(1, args.repeats)):
+        launches0 = s.info()["kernel_launches"]
+        barrier()
+        s.timer_start()
+        s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)              # exactly K timed steps
+        rep_ms = s.timer_stop()
+        barrier()
+        launches = s.info()["kernel_launches"] - launches0
+        if dist is not None:                                         # a repeat takes as long as its slowest rank
+            import torch
+            tt = torch.tensor([rep_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            rep_ms = float(tt[0])
+        repeats_ms.append(rep_ms)
     clocks = sampler.stop()
+    ms = float(np.median(repeats_ms))
 
     # per-kernel device time of the fused stage kernels, CUDA events on the launching stream
     s.profile_begin()
@@ -358,9 +463,9 @@ def run_ours(args):
 
     if dist is not None:
         import torch
-        tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_s * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(tt[0]), float(tt[1])
+        e2e_ms = float(tt[0])
     else:
         e2e_ms = e2e_s * 1e3
 
@@ -385,9 +490,13 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "repeats": {"n": len(repeats_ms), "ms_per_step": [r / args.steps for r in repeats_ms],
+                        "spread": (max(repeats_ms) - min(repeats_ms)) / ms, "reported": "median",
+                        "timed_seconds_total": sum(repeats_ms) * 1e-3},
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(dims, gdims, (px, py, pz)),
             "clocks": clocks,
+            "parity": parity,
             "gpu_launches": int(launches),
             "e2e": {"value": cells_total * 3.0 * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": nbytes / args.steps, "d2h_bytes_per_step": nbytes / args.steps + 88,

@@ -68,8 +68,8 @@ void downloadForOutput(mmf_ctx *ctx, int order, bool haveStep, CellStorageDouble
 void refreshPrimitives(mmf_ctx *ctx, const std::vector<std::size_t> &cellRawIds, const CellStorageDouble &cons,
                        CellStorageDouble *prim)
 {
-    // (opt-in until the entry point has run on a GPU: MMF_DEVICE_PRIMITIVES=1; otherwise the reference's host loop)
-    static const bool onDevice = std::getenv("MMF_DEVICE_PRIMITIVES") && std::atoi(std::getenv("MMF_DEVICE_PRIMITIVES"));
+    // (MMF_DEVICE_PRIMITIVES=0: the reference's host loop instead)
+    static const bool onDevice = !(std::getenv("MMF_DEVICE_PRIMITIVES") && std::atoi(std::getenv("MMF_DEVICE_PRIMITIVES")) == 0);
     if (ctx && onDevice) {
         if (mmf_get_primitives(ctx, MMF_FIELD_U, prim->rawData(0)) != MMF_OK) mmf_b200::fail("mmf_get_primitives", ctx);
         return;

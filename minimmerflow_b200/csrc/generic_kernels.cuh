@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) generic_rk_kernel(int64_t n_cells, int64_
     }
 }
 
-// Residual and RK stage in one pass for stages 2 and 3 (opt-in, MMF_GENERIC_FUSED=1): every thread forms its
+// Residual and RK stage in one pass for stages 2 and 3 (the default of a fused step; MMF_GENERIC_FUSED=0 turns it off): every thread forms its
 // cell's residual exactly like generic_rhs_kernel and applies the stage loop of src/main.cpp:445-459 / 481-495
 // to it right away, so the residual is neither written nor read back between the two.  Stage 1 stays unfused:
 // its dt is chosen from its own residual's face maximum (src/main.cpp:398-402).

@@ -112,7 +112,9 @@ static int create_generic(mmf_ctx *ctx, const mmf_mesh_desc *d)
         MMF_CUDA(ctx, cudaMemset(ctx->fields[i], 0, sizeof(double) * NF * g.stride));
     }
     // (not for a description with a boundary condition between two solved cells, see generic_tables.h)
-    ctx->generic_fused = getenv("MMF_GENERIC_FUSED") && atoi(getenv("MMF_GENERIC_FUSED")) != 0 && !t.bc_between_solved;
+    // stages 2 and 3 as one kernel each (bit-exact on the GPU, 10 % faster per step at 128^3: profiles/r02c_experiments.md);
+    // MMF_GENERIC_FUSED=0 restores the unfused sequence
+    ctx->generic_fused = !(getenv("MMF_GENERIC_FUSED") && atoi(getenv("MMF_GENERIC_FUSED")) == 0) && !t.bc_between_solved;
     if (ctx->generic_fused) {
         if ((rc = dev_alloc(ctx, &ctx->w_alt, (size_t) NF * g.stride))) return rc;
         MMF_CUDA(ctx, cudaMemset(ctx->w_alt, 0, sizeof(double) * NF * g.stride));
@@ -334,7 +336,7 @@ extern "C" int mmf_compute_polynomials(mmf_ctx *ctx, int field)
 }
 
 // residual of `field` into RHS, face-max eigenvalue into ctl->max_eig[slot]; no synchronisation
-// derived: the fused sequence's variant of the generic residual kernel (MMF_GENERIC_FUSED=1, step_enqueue only)
+// derived: the fused sequence's variant of the generic residual kernel (the default sequence of step_enqueue; MMF_GENERIC_FUSED=0 turns it off)
 static int rhs_enqueue(mmf_ctx *ctx, int field, int slot, bool derived = false)
 {
     double *d_max = &ctx->d_ctl->max_eig[slot];
@@ -369,7 +371,7 @@ static int rk_enqueue(mmf_ctx *ctx, int stage)
     return MMF_OK;
 }
 
-// stages 2 and 3 of the generic path as one kernel each (MMF_GENERIC_FUSED=1)
+// stages 2 and 3 of the generic path as one kernel each (default; MMF_GENERIC_FUSED=0: the unfused sequence)
 static int generic_stage_enqueue(mmf_ctx *ctx, int stage)
 {
     double *d_max = &ctx->d_ctl->max_eig[stage - 1];

@@ -39,7 +39,7 @@ struct mmf_ctx {
     // generic path
     mmf::GenericMesh gm{};
     double *fields[3] = { nullptr, nullptr, nullptr }; // SoA, 5*stride each
-    // MMF_GENERIC_FUSED=1 (opt-in until it has run on a GPU): stages 2 and 3 of a step as one kernel each
+    // stages 2 and 3 of a step as one kernel each (default; MMF_GENERIC_FUSED=0 turns it off)
     // (generic_stage_kernel); stage 2 then writes the second work array and the two swap roles
     bool generic_fused = false;
     double *w_alt = nullptr;

@@ -60,9 +60,15 @@ struct XGhost {
 // kernel runs, and a non-coherent L1 line fetched earlier on the same SM could hold the old values
 __device__ __forceinline__ double ldsin(const double *p) { return __ldcg(p); }
 
+// Position of cell 0 in a padded row.  Two, not one: a row then reads [pad][ghost][cells 0 .. nx-1][ghost][pad ...]
+// and cell 0 sits on a 16-byte boundary (rows are multiples of 32 bytes), which is what a bulk tensor (TMA) store
+// needs for the start of a box of 8-byte elements; the x windows of the stage kernels start at even cells.
+constexpr int XOFF = 2;
+__host__ __device__ constexpr int padded_row(int nx) { return (nx + XOFF + 1 + 3) / 4 * 4; }
+
 __host__ __device__ __forceinline__ long long uoff(const UniformGeom &g, int i, int j, int k)
 {
-    return ((long long) (k + 1) * g.py + (j + 1)) * g.px + (i + 1);
+    return ((long long) (k + 1) * g.py + (j + 1)) * g.px + (i + XOFF);
 }
 
 // ---- per-cell derived quantities ---------------------------------------------------------------
@@ -212,7 +218,7 @@ __device__ __forceinline__ double wall_cell_update(const UniformGeom &g, const L
                                                    const long long o, const double dt, double *out)
 {
     const long long plane = (long long) g.py * g.px;
-    const int k = (int) (o / plane) - 1, j = (int) ((o % plane) / g.px) - 1, i = (int) (o % g.px) - 1;
+    const int k = (int) (o / plane) - 1, j = (int) ((o % plane) / g.px) - 1, i = (int) (o % g.px) - XOFF;
     const int ijk[3] = { i, j, k }, gijk[3] = { g.gx0 + i, g.gy0 + j, g.gz0 + k }, ext[3] = { g.nx, g.ny, g.nz };
     const long long step[3] = { 1, g.px, plane };
     // processing order of the six face slots (0 -x, 1 +x, 2 -y, 3 +y, 4 -z, 5 +z)

@@ -14,22 +14,15 @@
 namespace mmf {
 
 // which stage-kernel form runs a stage and with how many warps per CTA:
-//   'p' ping-pong low-face kernel (uniform_stage_v5.cuh), 'r' its rotate form (uniform_stage_v5r.cuh),
-//   'd' the rotate form with the y exchange decoupled by one plane (uniform_stage_v6.cuh; opt-in until it
-//       has been measured on the GPU), 'h' the same with ONE warp serving both halo rows (a CTA updates
-//       nw-1 rows instead of nw-2; opt-in likewise), 'w' the merged-halo decoupled kernel with TWO y rows per
-//       warp (uniform_stage_v7.cuh: 2 (nw-1) rows per CTA, 8 warps; opt-in likewise), '3' the older
-//       high-face kernel (uniform_stage_v3.cuh, 12 warps), kept as an independent cross-check, 'b' the rotate
-//       form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never by
-//       MMF_STAGE_CFG), 'c' the same with the wall cells recomputed by a small pass around the stage kernel
-//       instead of a slow path inside it
+//   'r' the rotate form of the low-face streaming kernel (uniform_stage_v5r.cuh), the default: 12 warps
+//   'm' the same with bulk tensor (TMA) stores of the output (opt-in: measured 6 % slower, see there)
+//   'c' the rotate form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never
+//       by MMF_STAGE_CFG), the wall cells recomputed by a small pass around the stage kernel
 struct StageShape {
-    char form = 'p';
-    int nw = 16;
+    char form = 'r';
+    int nw = 12;
     int lz = 0; // planes per CTA
-    // y rows a CTA updates: all warps but the two halo rows; forms 'h' and 'w' serve both halo rows with
-    // one warp, and every other warp of form 'w' owns two rows
-    int rows() const { return form == 'w' ? 2 * (nw - 1) : form == 'h' ? nw - 1 : nw - 2; }
+    int rows() const { return nw - 2; } // y rows a CTA updates: all warps but the two halo rows
     StageShape() = default;
     StageShape(char f, int n) : form(f), nw(n) {}
 };
@@ -46,15 +39,16 @@ struct UniformPath {
     float *cta_est = nullptr;         // per stage-3 tile: FP32 estimate of the max eigenvalue of what it wrote
     int *eig_cand = nullptr;          // [0] = number of listed tiles, then their indices
     int n_tiles3 = 0;
+    // kernel form 'm': bulk tensor stores; one descriptor per state array (U, Wa, Wb, RHS), built with the array
+    TmaDesc out_map[4];
+    bool out_map_ok[4] = { false, false, false, false };
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
-    bool clamp_ff = true;             // no stage runs the v3 form: free-flow ghosts are never read
-    // bodies (opt-in, MMF_UNIFORM_BODIES=1): one flag per padded cell, 1 = not solved (src/main.cpp:221-237);
-    // the ghost shell repeats the flag of the cell it touches
+    bool clamp_ff = true;             // free-flow ghosts are never read by the stage kernels (LoadClamp)
+    // bodies: one flag per padded cell, 1 = not solved (src/main.cpp:221-237), 2 = fluid cell with a wall interface,
+    // which the stage kernel does not store and wall_cell_update recomputes (list of their padded offsets, compact
+    // result buffer); the ghost shell repeats the flag of the cell it touches
     unsigned char *solid = nullptr;
-    bool bodies = false;              // set before the arrays are laid out: selects kernel form 'b' for every stage
-    // MMF_UNIFORM_BODIES=2: form 'c' instead -- flag 2 marks the fluid cells with a wall interface, which the stage
-    // kernel does not store and wall_cell_update recomputes (list of their padded offsets, compact result buffer)
-    bool bodies_fixup = false;
+    bool bodies = false;              // set before the arrays are laid out: selects kernel form 'c' for every stage
     int *wall_list = nullptr;
     int n_wall = 0;
     double *wall_compact = nullptr;
@@ -95,7 +89,7 @@ static bool uniform_use_xghost(const mmf_ctx *ctx)
     if (u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0) return false;
     for (int st = 0; st < 4; ++st) {
         const StageShape &sh = u->shape[st];
-        if (sh.form == 'w' ? sh.nw != 8 : (sh.nw != 12 && sh.nw != 16)) return false;
+        if (sh.nw != 12 && sh.nw != 16) return false;
     }
     return true;
 }
@@ -126,23 +120,6 @@ static cudaError_t stage_smem_attribute(K kern, size_t smem)
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess) done.emplace_back((const void *) kern, dev);
     return e;
-}
-
-template <typename K>
-static int launch_stage_v3(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const UniformGeom &g = u->g;
-    const int nw = 12, lz = u->shape[stage].lz;
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + (nw - 2) - 1) / (nw - 2), (g.nz + lz - 1) / lz);
-    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
-    {
-        ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz);
-    }
-    MMF_LAUNCH_CHECK(ctx);
-    return MMF_OK;
 }
 
 template <typename K>
@@ -191,14 +168,100 @@ static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, 
     return MMF_OK;
 }
 
-// form 'b' (a box with bodies, single GPU): the 12-warp rotate-form geometry plus the flag array
+// ---- bulk tensor stores (kernel form 'm') ------------------------------------------------------------------------
+// The descriptor of one padded state array for STORES: dimensions (x, y, z, field) = (nx, ny, nz, NF) with element
+// (0, 0, 0, f) at cell (0, 0, 0) of field f -- 16-byte aligned because cell 0 sits at column XOFF = 2 of a padded row,
+// and every x window starts at an even cell, which the start of a box of 8-byte elements needs -- and a box of
+// XW x 1 x 1 x NF: everything a ragged tile writes beyond the box of cells is clipped by the hardware.  cuTensorMapEncodeTiled comes from the driver through the runtime
+// (cudaGetDriverEntryPoint): the library does not link libcuda.
+static int uniform_make_out_map(mmf_ctx *ctx, double *arr, TmaDesc *map)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MMF_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const UniformGeom &g = ctx->uni->g;
+    static_assert(XOFF % 2 == 0 && XW % 2 == 0, "bulk tensor stores of doubles start at even columns");
+    const cuuint64_t dims[4] = { (cuuint64_t) g.nx, (cuuint64_t) g.ny, (cuuint64_t) g.nz, (cuuint64_t) NF };
+    const cuuint64_t strides[3] = { (cuuint64_t) g.px * 8, (cuuint64_t) g.px * g.py * 8, (cuuint64_t) g.fs * 8 }; // bytes, dims 1..3
+    const cuuint32_t box[4] = { (cuuint32_t) XW, 1, 1, (cuuint32_t) NF };
+    const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    void *base = arr + uoff(g, 0, 0, 0);
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d box", (int) r, g.nx, g.ny, g.nz);
+    return MMF_OK;
+}
+
+// launch_stage_k for the kernels that take the output's tensor descriptor as their last argument
+template <typename K>
+static int launch_stage_ts(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
+                           double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    int a = -1;
+    for (int q = 0; q < 4; ++q) if (Out == u->arr[q]) a = q;
+    if (a < 0) return fail(ctx, MMF_ERR_INVALID, "bulk tensor stores: the output is not one of the state arrays");
+    if (!u->out_map_ok[a]) {
+        if (int rc = uniform_make_out_map(ctx, u->arr[a], &u->out_map[a])) return rc;
+        u->out_map_ok[a] = true;
+    }
+    const int lz = u->shape[stage].lz, rows = u->shape[stage].rows();
+    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
+    for (int q = 0; q < 3; ++q) {
+        if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
+            MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
+            u->push_pending[q] = false;
+        }
+    }
+    HaloWait hw{};
+    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
+    if (ctx->comm && u->p2p && u->halo_inkernel) {
+        int ain = -1;
+        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) ain = q;
+        for (int s = 0; s < 6; ++s) hw.mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
+        if (ain >= 0 && hw.mask) {
+            hw.flags = u->flags;
+            hw.seq = u->arr_seq[ain];
+            hw.tile_order = u->tile_order[stage];
+            if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+        }
+    }
+    XGhost xg{};
+    if (hw.flags && uniform_use_xghost(ctx)) { // x ghosts of partition sides come from the compact columns
+        int ain = 0;
+        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) ain = q;
+        xg.fs = u->xg_fs;
+        xg.pitch = g.ny + 2;
+        if (u->nbr_rank[0] >= 0) xg.lo = u->xghost + (size_t) (0 * 3 + ain) * NF * u->xg_fs;
+        if (u->nbr_rank[1] >= 0) xg.hi = u->xghost + (size_t) (1 * 3 + ain) * NF * u->xg_fs;
+    }
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
+                                                   uniform_load_clamp(u), hw, xg, u->out_map[a]);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
+// form 'c' (a box with bodies, single GPU): the 12-warp rotate-form geometry plus the flag array
 template <typename K>
 static int launch_stage_body(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
     const int nw = 12, lz = u->shape[stage].lz, rows = u->shape[stage].rows();
-    if (!u->solid) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'b' needs the flag array of a box with bodies");
+    if (!u->solid) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'c' needs the flag array of a box with bodies");
     dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
     const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
     MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
@@ -224,31 +287,20 @@ typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const d
     int MMF_STAGE_TU_NAME(F, 1)(mmf_ctx *, int, const double *, const double *, double *, double *);   \
     int MMF_STAGE_TU_NAME(F, 2)(mmf_ctx *, int, const double *, const double *, double *, double *);   \
     int MMF_STAGE_TU_NAME(F, 3)(mmf_ctx *, int, const double *, const double *, double *, double *);
-MMF_DECLARE_STAGE_TUS(p)  // uniform_stage_v5.cuh
 MMF_DECLARE_STAGE_TUS(r)  // uniform_stage_v5r.cuh
-MMF_DECLARE_STAGE_TUS(d)  // uniform_stage_v6.cuh
-MMF_DECLARE_STAGE_TUS(h)  // uniform_stage_v6.cuh, one warp for both halo rows
-MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_v3.cuh (form '3')
-MMF_DECLARE_STAGE_TUS(w)  // uniform_stage_v7.cuh, two y rows per warp
-MMF_DECLARE_STAGE_TUS(b)  // uniform_stage_v5rb.cuh, a box with bodies
-MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies, wall cells by a fix-up pass
+MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies
+MMF_DECLARE_STAGE_TUS(m)  // uniform_stage_v5r.cuh with bulk tensor stores
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('p', 'r', 'd', 'h', 'w', '3', 'b', 'c') for a stage
+// the launcher of a kernel form ('r', 'c', 'm') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[8][4] = {
-        { launch_stage_p_0, launch_stage_p_1, launch_stage_p_2, launch_stage_p_3 },
+    static const StageLauncher tab[3][4] = {
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
-        { launch_stage_d_0, launch_stage_d_1, launch_stage_d_2, launch_stage_d_3 },
-        { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
-        { launch_stage_h_0, launch_stage_h_1, launch_stage_h_2, launch_stage_h_3 },
-        { launch_stage_w_0, launch_stage_w_1, launch_stage_w_2, launch_stage_w_3 },
-        { launch_stage_b_0, launch_stage_b_1, launch_stage_b_2, launch_stage_b_3 },
         { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
+        { launch_stage_m_0, launch_stage_m_1, launch_stage_m_2, launch_stage_m_3 },
     };
-    const int f = (form == 'r') ? 1 : (form == 'd') ? 2 : (form == '3') ? 3 : (form == 'h') ? 4 : (form == 'w') ? 5 : (form == 'b') ? 6 : (form == 'c') ? 7 : 0;
-    return tab[f][stage];
+    return tab[(form == 'c') ? 1 : (form == 'm') ? 2 : 0][stage];
 }
 
 } // namespace mmf

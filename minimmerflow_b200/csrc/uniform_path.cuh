@@ -108,7 +108,7 @@ static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, dou
 static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
 {
     UniformGeom &g = u->g;
-    g.px = (g.nx + 2 + 3) / 4 * 4;
+    g.px = padded_row(g.nx);
     g.py = g.ny + 2;
     g.pz = g.nz + 2;
     g.fs = ((long long) g.px * g.py * g.pz + 15) / 16 * 16;
@@ -120,13 +120,10 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         fill_benign_kernel<<<grid_for(g.fs, 256), 256, 0, ctx->stream>>>(u->arr[a], g.fs);
         MMF_LAUNCH_CHECK(ctx);
     }
-    // Launch shapes, measured at 256^3 on B200 (profiles/): the ping-pong form at 16 warps (128
-    // registers) is the fastest stage-1 / RHS-only kernel, the rotate form at 12 warps (164-166
-    // registers, no spills) the fastest for stages 2 and 3, which also stream U^n.
-    // MMF_STAGE_CFG overrides, e.g. "p16:p16:r12:r12" (stage 0:1:2:3), "d12" = the decoupled form
-    // everywhere, "h12" = decoupled with a merged halo warp, "w8" = two y rows per warp, "312" = v3 everywhere.
-    const StageShape defaults[4] = { { 'p', 16 }, { 'p', 16 }, { 'r', 12 }, { 'r', 12 } };
-    for (int st = 0; st < 4; ++st) u->shape[st] = defaults[st];
+    // Launch shapes, measured at 256^3 on B200 (profiles/r02c_experiments.md): the rotate form at 12 warps (158-166
+    // registers, no spills) is the fastest kernel of every stage.  MMF_STAGE_CFG overrides per stage, e.g.
+    // "r12:r16:m12:m12" (stage 0:1:2:3; 'm' = the same kernel with bulk tensor stores, 12 warps).
+    for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'r', 12 };
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
         int st = 0;
         for (const char *p = cfg; *p && st < 4;) {
@@ -136,21 +133,19 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'p' && sh.form != 'r' && sh.form != 'd' && sh.form != 'h' && sh.form != 'w' && sh.form != '3') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
-            if (sh.form == '3') sh.nw = 12;
-            if (sh.form == 'w') sh.nw = 8;  // two rows per warp: 8 warps at 248 registers
+            if ((sh.form != 'r' && sh.form != 'm') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if (sh.form == 'm') sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }
     }
     if (u->bodies) { // a box with bodies: the one kernel form that knows about them, whatever MMF_STAGE_CFG says
-        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ u->bodies_fixup ? 'c' : 'b', 12 };
+        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'c', 12 };
     }
     // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
     // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
     // derives for its first z interface; chunks stay between 16 and 96 planes.
     u->clamp_ff = true;
-    for (int st = 0; st < 4; ++st) u->clamp_ff = u->clamp_ff && u->shape[st].form != '3';
     u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));
     const char *env_lz = getenv("MMF_STAGE_LZ");
     for (int st = 0; st < 4; ++st) {
@@ -235,14 +230,14 @@ static int uniform_create(mmf_ctx *ctx, const mmf_uniform_desc *d)
 }
 
 // Decide whether a host mesh description is a full, conforming, uniform 3-D box whose interface numbering
-// matches a known convention; if so build the uniform path from it.  All cells solved -- or, opt-in until the
-// kernel has run on the GPU (MMF_UNIFORM_BODIES=1), a box with bodies: cells that are not solved, and BC_WALL
-// on exactly the interfaces between a solved and an unsolved cell (src/main.cpp:221-237, 251-277).
+// matches a known convention; if so build the uniform path from it.  All cells solved, or a box with bodies:
+// cells that are not solved, and BC_WALL on exactly the interfaces between a solved and an unsolved cell
+// (src/main.cpp:221-237, 251-277).  MMF_UNIFORM_BODIES=0 keeps a mesh with bodies on the generic path.
 static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
 {
     *used = false;
-    // (bodies: opt-in until the kernels have run on the GPU, MMF_UNIFORM_BODIES=1 / 2; single GPU)
-    const bool allow_bodies = getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) && !ctx->comm;
+    // (a handle is created before it can join a communicator: comm_set_box_neighbours rejects a box with bodies)
+    const bool allow_bodies = !(getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) == 0);
     const UniformBoxAnalysis an = analyze_uniform_box(d, allow_bodies);
     if (!an.eligible) return MMF_OK;
     const int nx = d->box_dims[0], ny = d->box_dims[1], nz = d->box_dims[2];
@@ -266,20 +261,17 @@ static int uniform_try_create(mmf_ctx *ctx, const mmf_mesh_desc *d, bool *used)
     u->iface_numbering = numbering;
     u->order_exact = order_exact;
     u->bodies = bodies;
-    u->bodies_fixup = bodies && atoi(getenv("MMF_UNIFORM_BODIES")) == 2;
     ctx->path = MMF_PATH_UNIFORM;
     int rc = uniform_alloc(ctx, u);
     if (rc) return rc;
     if (bodies) {
         std::vector<unsigned char> flag;
         std::vector<int> walls;
-        body_flags(g, nc, d->cell_ijk, d->solved, u->bodies_fixup, flag, walls);
-        if (u->bodies_fixup) {
-            u->n_wall = (int) walls.size();
-            if (walls.empty()) walls.push_back(0);
-            if ((rc = dev_upload(ctx, &u->wall_list, walls))) return rc;
-            if ((rc = dev_alloc(ctx, &u->wall_compact, (size_t) NF * walls.size()))) return rc;
-        }
+        body_flags(g, nc, d->cell_ijk, d->solved, true, flag, walls);
+        u->n_wall = (int) walls.size();
+        if (walls.empty()) walls.push_back(0);
+        if ((rc = dev_upload(ctx, &u->wall_list, walls))) return rc;
+        if ((rc = dev_alloc(ctx, &u->wall_compact, (size_t) NF * walls.size()))) return rc;
         if ((rc = dev_upload(ctx, &u->solid, flag))) return rc;
     }
     std::vector<int> off((size_t) nc);
@@ -407,7 +399,7 @@ static int uniform_step(mmf_ctx *ctx)
     trace_point(ctx, "stage3");
     u->w_cur = 2;
     const StageShape &s3 = u->shape[3];
-    if (s3.form != '3' && !u->bodies) {
+    if (!u->bodies) {
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
         const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.rows() - 1) / s3.rows();

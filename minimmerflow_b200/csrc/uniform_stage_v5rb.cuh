@@ -1,5 +1,6 @@
 // uniform_stage_v5rb.cuh -- the rotate-form stage kernel (uniform_stage_v5r.cuh) for a uniform box WITH
-// BODIES (kernel form 'b'; opt-in until it has run on the GPU: MMF_UNIFORM_BODIES=1).
+// BODIES (kernel form 'c'; the path picks it by itself for such a mesh, MMF_UNIFORM_BODIES=0 sends the mesh to the
+// generic path instead).
 //
 // The reference marks the cells whose centroid lies inside a body box as not solved (src/main.cpp:221-237,
 // src/body.cpp:80-95), gives every interface between a fluid and a solid cell BC_WALL (src/main.cpp:251-277)
@@ -9,82 +10,32 @@
 // (:237-247); the RK loops skip the cells that are not solved (src/main.cpp:409-423).  The interface ids,
 // hence the accumulation order of a fluid cell, do not depend on any of this.
 //
-// Here the flag travels with the data every face evaluation already receives: a solid cell reports a
-// NEGATIVE max eigenvalue (lam = -1; a real one is |u_n| + a > 0) in the x shuffle, in the y record and in
-// the carried z state.  A face whose two sides agree is the ordinary two-cell flux (solid | solid yields a
-// value that only ever reaches solid cells, which are never stored, and lam = -1 never raises a maximum);
-// a face whose sides differ takes a slow path -- a call, so that the hot path keeps its registers -- that
-// rebuilds both sides from the fluid cell's state exactly as the reference does.  Walls are a surface: the
-// slow path runs for a few lanes of a few warps.  One byte per cell of extra traffic (the padded flag array).
+// The flag travels with the data every face evaluation already receives: a solid cell reports a NEGATIVE max
+// eigenvalue (lam = -1; a real one is |u_n| + a > 0) in the x shuffle, in the y record and in the carried z
+// state (lam = -1 never raises a maximum).  This kernel evaluates a wall like any interface and does not store
+// the cells that touch one (flag 2) nor the solid ones (flag 1): the wall cells -- a surface -- are recomputed
+// reference-shaped by wall_cell_update (uniform_device.cuh; uniform_wall_cells_kernel before the stage kernel,
+// uniform_wall_scatter_kernel behind it), so the hot path has no slow path, no call and no divergent branch.
+// One byte per cell of extra traffic (the padded flag array).  Measured at 128^3 with two bodies (round 2): 0.43 ms
+// per step against 0.29 ms without bodies and 1.60 ms on the generic path; the variant with the wall evaluation
+// inside the kernel (a call at each face whose sides differ: spills around three call sites per plane) took 0.86 ms
+// and was removed.
 #pragma once
 
 #include "uniform_stage_v5r.cuh"
 
 namespace mmf {
 
-// The wall slow path is a call by default: ptxas then spills around three call sites per plane (472 bytes, 48
-// local-memory instructions per plane statically at stage 2).  -DMMF_WALL_INLINE=__forceinline__ (Makefile
-// EXTRA=..., OUT=... for a second library) inlines it instead: 124 bytes of spill, 22 local-memory
-// instructions, but three copies of the path in the plane loop (2090 instead of 814 instructions per plane).
-// Which one is faster is a measurement the first GPU call on this form has to make.
-#ifndef MMF_WALL_INLINE
-#define MMF_WALL_INLINE __noinline__
-#endif
-struct WallFlux {
-    double AF[NF];
-    double lam;
-};
-
-template <int AXIS>
-__device__ __forceinline__ void wall_side(const double *U, const DivConsts &dc, double *F, double &lam)
-{
-    CellPrim q;
-    derive_cell(U, dc, q);
-    axis_flux<AXIS>(q, F, lam);
-}
-
-// area * LLF flux of a wall interface with normal +e_axis (owner = the low cell) from the fluid cell's
-// conservative state.  fluid_is_low: the fluid cell is the owner, the boundary condition sees the interface
-// normal; otherwise it sees the flipped normal -1.*n (src/euler.cpp:205-224), the splitting the un-flipped
-// one (:232).
-static __device__ MMF_WALL_INLINE WallFlux wall_face(const int axis, const int fluid_is_low, const double u0, const double u1,
-                                           const double u2, const double u3, const double u4, const double Ah,
-                                           const double y_gm1, const double y_c1)
-{
-    const double fu[NF] = { u0, u1, u2, u3, u4 };
-    DivConsts dc;
-    dc.y_gm1 = y_gm1; dc.y_c1 = y_c1; dc.y_vol = 0.0;
-    double n[3] = { 0.0, 0.0, 0.0 };
-    n[axis] = 1.0;
-    double bn[3] = { n[0], n[1], n[2] };
-    if (!fluid_is_low) { bn[0] = -1. * n[0]; bn[1] = -1. * n[1]; bn[2] = -1. * n[2]; }
-    double vu[NF];
-    interface_bc_values(BC_WALL, bn, nullptr, fu, vu);
-    double fF[NF], fl, vF[NF], vl;
-    if (axis == 0)      { wall_side<0>(fu, dc, fF, fl); wall_side<0>(vu, dc, vF, vl); }
-    else if (axis == 1) { wall_side<1>(fu, dc, fF, fl); wall_side<1>(vu, dc, vF, vl); }
-    else                { wall_side<2>(fu, dc, fF, fl); wall_side<2>(vu, dc, vF, vl); }
-    WallFlux r;
-    r.lam = fluid_is_low ? llf_area_flux(fu, fF, fl, vu, vF, vl, Ah, r.AF) : llf_area_flux(vu, vF, vl, fu, fF, fl, Ah, r.AF);
-    return r;
-}
-
-// the interface (low | high) along AXIS; a negative lam marks a solid side.  FIXUP (kernel form 'c'): a wall is
-// evaluated like any interface here -- the fluid cell it belongs to is not stored by this kernel but recomputed
-// by wall_cell_update (uniform_device.cuh) -- so the hot path has no call and no divergent branch; the value of
+// the interface (low | high) along AXIS; a negative lam marks a solid side.  A wall is evaluated like any interface
+// here -- the fluid cell it belongs to is not stored by this kernel but recomputed by wall_cell_update -- and the value
 // max(lam_fluid, -1) = lam_fluid it contributes to the face maximum is one the true maximum contains anyway.
 template <int AXIS, bool FIXUP>
 __device__ __forceinline__ double body_face_flux(const double *LU, const double *LF, const double ll, const double *HU,
-                                                 const double *HF, const double hl, const double Ah, const DivConsts &dc,
+                                                 const double *HF, const double hl, const double Ah, const DivConsts &,
                                                  double *AF)
 {
-    const bool sl = ll < 0.0, sh = hl < 0.0;
-    if (FIXUP || sl == sh) return llf_area_flux(LU, LF, ll, HU, HF, hl, Ah, AF);
-    const WallFlux w = wall_face(AXIS, sh ? 1 : 0, sh ? LU[0] : HU[0], sh ? LU[1] : HU[1], sh ? LU[2] : HU[2],
-                                 sh ? LU[3] : HU[3], sh ? LU[4] : HU[4], Ah, dc.y_gm1, dc.y_c1);
-#pragma unroll
-    for (int k = 0; k < NF; ++k) AF[k] = w.AF[k];
-    return w.lam;
+    static_assert(FIXUP, "the in-kernel wall evaluation was removed: wall cells are recomputed by wall_cell_update");
+    return llf_area_flux(LU, LF, ll, HU, HF, hl, Ah, AF);
 }
 
 template <int STAGE, int ORDER, int NW, bool FIXUP>
@@ -130,7 +81,7 @@ uniform_stage_kernel_v5rb(const UniformGeom g, const double *__restrict__ Sin, c
 
     const long long plane = (long long) g.py * g.px;
     const long long fs    = g.fs;
-    const long long col   = (long long) (jc + 1) * g.px + (ic + 1);
+    const long long col   = (long long) (jc + 1) * g.px + (ic + XOFF);
     const double *scol = Sin + col;
     const unsigned char *mcol = solid + col; // the flag array has the layout of one field
     double lmax = 0.0;

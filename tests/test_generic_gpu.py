@@ -12,10 +12,6 @@ import os
 
 pytestmark = pytest.mark.gpu
 
-# MMF_GENERIC_FUSED=1 (stages 2 and 3 as one kernel each, generic_stage_kernel) has been checked on the CPU
-# emulator only (tests/test_emu_generic.py): opt-in until its first GPU run, like the unmeasured stage-kernel forms
-EXPERIMENTAL = os.environ.get("MMF_TEST_EXPERIMENTAL", "0") not in ("", "0")
-_exp = pytest.mark.skipif(not EXPERIMENTAL, reason="generic fused stages: set MMF_TEST_EXPERIMENTAL=1")
 
 GENERIC = 1  # MMF_FLAG_FORCE_GENERIC
 
@@ -220,12 +216,13 @@ def test_run_respects_max_steps_and_tmax_clamp(mmf, oracle):
     assert ref["t"] == t
 
 
-@_exp
+@pytest.mark.parametrize("fused", ["1", "0"])
 @pytest.mark.parametrize("kind", ["vortex2d", "bodies3d", "hanging3d"])
-def test_generic_fused_stages_bit_exact(mmf, oracle, monkeypatch, kind):
-    """MMF_GENERIC_FUSED=1: residual + RK update of stages 2 and 3 in one kernel each, two work arrays swapping
-    roles; dt, the three logged eigenvalues, U, W and the stage-3 residual left in RHS are those of the oracle."""
-    monkeypatch.setenv("MMF_GENERIC_FUSED", "1")
+def test_generic_fused_stages_bit_exact(mmf, oracle, monkeypatch, kind, fused):
+    """The generic path's step: residual + RK update of stages 2 and 3 in one kernel each, two work arrays swapping
+    roles (the default) and the unfused sequence (MMF_GENERIC_FUSED=0); dt, the three logged eigenvalues, U, W and
+    the stage-3 residual left in RHS are those of the oracle."""
+    monkeypatch.setenv("MMF_GENERIC_FUSED", fused)
     if kind == "vortex2d":
         m = oracle.problem_mesh("vortex_xy", 2, 64)
         U = oracle.init_state(m)
@@ -239,7 +236,7 @@ def test_generic_fused_stages_bit_exact(mmf, oracle, monkeypatch, kind):
         rng = np.random.default_rng(11)
         rho = rng.uniform(0.5, 1.5, nc); vel = rng.uniform(-0.4, 0.4, (nc, 3)); p = rng.uniform(0.6, 1.4, nc)
         U = np.column_stack([rho, rho * vel[:, 0], rho * vel[:, 1], rho * vel[:, 2], p / 0.4 + 0.5 * rho * (vel ** 2).sum(1)])
-    with _solver(mmf, m) as s:
+    with _solver(mmf, m, flags=mmf.FLAG_FORCE_GENERIC) as s:
         assert s.info()["path"] == mmf.PATH_GENERIC
         s.set_state(mmf.FIELD_U, U)
         s.set_state(mmf.FIELD_W, U)

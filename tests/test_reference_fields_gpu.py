@@ -1,7 +1,7 @@
 """GPU parity against the REFERENCE's own final fields (tests/golden/reference_fields.npz, written by
 the unmodified reference sources): the device-resident time loop (mmf_run, what replaces
 src/main.cpp:377-506) must end on bitwise the same state, after the same number of steps, on every
-case -- 2-D, bodies / BC_WALL, BC_DIRICHLET included (generic path) and the plain 3-D boxes (fused
+case -- 2-D (generic path) and the 3-D boxes, plain, with bodies / BC_WALL and with BC_DIRICHLET (fused
 uniform path)."""
 import os
 
@@ -20,8 +20,8 @@ def test_resident_run_matches_reference_fields(mmf, oracle, case):
     n = case["name"]
     m = case_mesh(oracle, case)
     with mmf.EulerSolver.from_mesh(m, dirichlet_info=dirichlet_info(case)) as s:
-        # a box with bodies takes the fused path only when asked to (kernel form 'b', MMF_UNIFORM_BODIES=1)
-        bodies_fused = os.environ.get("MMF_UNIFORM_BODIES", "0") not in ("", "0")
+        # every 3-D box takes the fused path, with bodies (kernel form 'c') or without, unless MMF_UNIFORM_BODIES=0
+        bodies_fused = os.environ.get("MMF_UNIFORM_BODIES", "1") not in ("", "0")
         fused = m["dim"] == 3 and (bodies_fused or not case.get("bodies"))
         assert s.info()["path"] == (mmf.PATH_UNIFORM if fused else mmf.PATH_GENERIC)
         s.set_state(mmf.FIELD_U, oracle.init_state(m))

@@ -59,23 +59,10 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
         assert eig == ref_eig and bits_equal(got, ref), problem
 
 
-# Stage-kernel forms that have not been measured on the GPU yet ('d', 'h' = uniform_stage_v6.cuh, 'w' =
-# uniform_stage_v7.cuh, checked on the CPU emulator of tools/emu only): opt-in, so that an unproven kernel can never turn the suite red.
-# MMF_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k fused_steps   is the first thing to run on them.
-EXPERIMENTAL = os.environ.get("MMF_TEST_EXPERIMENTAL", "0") not in ("", "0")
-_exp = pytest.mark.skipif(not EXPERIMENTAL, reason="experimental stage-kernel form: set MMF_TEST_EXPERIMENTAL=1")
-EXPERIMENTAL_CFGS = [pytest.param(c, marks=_exp) for c in ("d12", "d16", "d8", "p16:d16:d12:d12", "d8:r12:d16:p8",
-                                                            "h12", "h16", "h8", "p16:h16:h12:h12", "h8:d12:h16:r8",
-                                                            "w8", "p16:w8:w8:w8", "w8:h12:w8:r12")]
-
-
 @pytest.mark.parametrize("lz", ["5", "1", "2"])
-@pytest.mark.parametrize("cfg", ["", "p12", "p16", "p8", "r12", "r16", "r8", "312", "r8:p12:r16:p8"] + EXPERIMENTAL_CFGS)
+@pytest.mark.parametrize("cfg", ["", "m12", "r16", "r8", "r8:m12:r16:r12"])
 def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
-    """Every stage-kernel form and CTA shape (default mix first), ragged z chunks; one- and two-plane
-    chunks for the forms that carry state from plane to plane."""
-    if lz != "5" and "d" not in cfg and "h" not in cfg and "w" not in cfg:
-        pytest.skip("one- and two-plane z chunks: the plane-decoupled forms only")
+    """Every stage-kernel form and CTA shape (default first), ragged z chunks down to one- and two-plane chunks."""
     if cfg:
         monkeypatch.setenv("MMF_STAGE_CFG", cfg)
     monkeypatch.setenv("MMF_STAGE_LZ", lz)           # ragged z chunks on purpose
@@ -95,7 +82,6 @@ def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
         assert bits_equal(s.get_state(mmf.FIELD_W), Wo)
 
 
-@_exp   # entry point added after the round's last GPU call: opt-in like the unmeasured kernel forms
 @pytest.mark.parametrize("generic", [False, True])
 def test_get_primitives_is_conservative2primitive(mmf, oracle, generic):
     """mmf_get_primitives = the utils::conservative2primitive loop src/main.cpp:511-518 runs before every
@@ -137,13 +123,11 @@ def _body_meshes(oracle):
     yield "box 37x29x11 + bodies", m
 
 
-@_exp
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch, mode):
-    """Kernel forms 'b' / 'c' (uniform_stage_v5rb.cuh, opt-in MMF_UNIFORM_BODIES=1 / 2; checked on the CPU emulator
-    only so far): a uniform box with bodies on the fused path -- RHS, the dt eigenvalue, ten fused steps and the
-    unfused operator sequence, bitwise against the oracle; cells that are not solved keep the host's values."""
-    monkeypatch.setenv("MMF_UNIFORM_BODIES", mode)
+def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
+    """Kernel form 'c' (uniform_stage_v5rb.cuh + wall_cell_update): a uniform box with bodies takes the fused path by
+    itself -- RHS, the dt eigenvalue, ten fused steps and the unfused operator sequence, bitwise against the oracle;
+    cells that are not solved keep the host's values."""
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
     rng = np.random.default_rng(11)
     for name, m in _body_meshes(oracle):
         nc = m["volume"].shape[0]
@@ -271,10 +255,17 @@ def test_axis_order_flag_is_within_tolerance_not_exact(mmf, oracle):
         assert max_rel_diff(s.get_state(mmf.FIELD_U), Uo) <= 1e-12
 
 
-def test_mesh_with_bodies_falls_back_to_generic(mmf, oracle, monkeypatch):
-    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)   # the fused body path is opt-in (forms b / c)
+def test_mesh_with_bodies_path_selection(mmf, oracle, monkeypatch):
+    """A uniform box with bodies takes the fused path (kernel form 'c'); MMF_UNIFORM_BODIES=0 and MMF_FLAG_FORCE_GENERIC
+    keep it on the generic one."""
     boxes = np.array([[3.0, 3.0, 3.0, 5.0, 5.0, 5.0]])
     m = oracle.problem_mesh("radsod", 3, 16, boxes=boxes)
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+    with mmf.EulerSolver.from_mesh(m, flags=mmf.FLAG_FORCE_GENERIC) as s:
+        assert s.info()["path"] == mmf.PATH_GENERIC
+    monkeypatch.setenv("MMF_UNIFORM_BODIES", "0")
     with mmf.EulerSolver.from_mesh(m) as s:
         assert s.info()["path"] == mmf.PATH_GENERIC
 

@@ -167,11 +167,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 }
 
 #include "uniform_stage_v5r.cuh"
-#ifdef MMF_EMU_HAVE_V6
-#include "uniform_stage_v6.cuh"
-#include "uniform_stage_v7.cuh"
 #include "uniform_stage_v5rb.cuh"
-#endif
 #include "uniform_eligibility.h"
 #include "generic_kernels.cuh"
 #include "generic_tables.h"
@@ -191,21 +187,27 @@ struct Args {
     LoadClamp lc;
     HaloWait hw;
     XGhost xg;
-    const unsigned char *solid; // form 'b': flag array of a box with bodies
+    const unsigned char *solid; // form 'c': flag array of a box with bodies
 };
+
+// the emulated descriptor of the output array for the bulk tensor stores of form 'm' (uniform_make_out_map)
+static TmaDesc out_desc(const Args &a)
+{
+    TmaDesc d{};
+    d.base = a.Out + uoff(a.g, 0, 0, 0);
+    d.stride[0] = 1; d.stride[1] = a.g.px; d.stride[2] = (long long) a.g.px * a.g.py; d.stride[3] = a.g.fs;
+    d.dim[0] = a.g.nx; d.dim[1] = a.g.ny; d.dim[2] = a.g.nz; d.dim[3] = NF;
+    d.box[0] = XW; d.box[1] = 1; d.box[2] = 1; d.box[3] = NF;
+    return d;
+}
 
 // compact x ghost columns (XG = true instantiations): the 12-warp shapes only, to bound the build time
 template <int STAGE, int ORDER>
 std::function<void()> bind_kernel_xg(int form, const Args &a)
 {
     switch (form) {
-    case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-#ifdef MMF_EMU_HAVE_V6
-    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, 12, true, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-#endif
+    case 'm': return [a] { uniform_stage_kernel_v5m<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg, out_desc(a)); };
     default: return nullptr;
     }
 }
@@ -215,15 +217,9 @@ std::function<void()> bind_kernel(int form, const Args &a)
 {
     if (a.xg.lo || a.xg.hi) return (NW == 12) ? bind_kernel_xg<STAGE, ORDER>(form, a) : nullptr;
     switch (form) {
-    case 'p': return [a] { uniform_stage_kernel_v5<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-#ifdef MMF_EMU_HAVE_V6
-    case 'd': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'h': return [a] { uniform_stage_kernel_v6<STAGE, ORDER, NW, false, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'w': return [a] { uniform_stage_kernel_v7<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
+    case 'm': return [a] { uniform_stage_kernel_v5m<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg, out_desc(a)); };
     case 'c': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
-#endif
     default: return nullptr;
     }
 }
@@ -282,13 +278,13 @@ void emu_set_xghost(const double *lo, const double *hi, long long fs, int pitch)
     g_xghost.lo = lo; g_xghost.hi = hi; g_xghost.fs = fs; g_xghost.pitch = pitch;
 }
 
-// flag array (padded layout of one field, 1 = not solved) for the NEXT emu_stage calls of form 'b'
+// flag array (padded layout of one field, 1 = not solved, 2 = wall cell) for the NEXT emu_stage calls of form 'c'
 void emu_set_solid(const unsigned char *solid) { g_solid = solid; }
 
 // padded extents of a box, as uniform_alloc (uniform_path.cuh) lays them out
 void emu_padded(const int dims[3], int pad[3], long long *fs)
 {
-    pad[0] = (dims[0] + 2 + 3) / 4 * 4;
+    pad[0] = mmf::padded_row(dims[0]);
     pad[1] = dims[1] + 2;
     pad[2] = dims[2] + 2;
     *fs = ((long long) pad[0] * pad[1] * pad[2] + 15) / 16 * 16;
@@ -322,7 +318,7 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     a.max_eig = max_eig;
     a.lz = lz;
     a.cta_est = cta_est;
-    const int rows = (form == 'w') ? 2 * (nw - 1) : (form == 'h') ? nw - 1 : nw - 2; // rows a tile updates
+    const int rows = nw - 2; // rows a tile updates
     const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + rows - 1) / rows, gz = (g.nz + lz - 1) / lz;
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;

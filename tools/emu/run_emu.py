@@ -5,7 +5,7 @@ hazards, buffer reuse races, index slips) before GPU time is spent on it.  Not a
 fallback, never timed; the GPU tests (tests/test_uniform_gpu.py) remain the parity proof.
 
     python tools/emu/run_emu.py                 # default matrix
-    python tools/emu/run_emu.py --forms d --nw 8,12 --chaos 300 --repeat 5
+    python tools/emu/run_emu.py --forms r,m --nw 8,12 --chaos 300 --repeat 5
 """
 import argparse
 import ctypes as C
@@ -16,6 +16,7 @@ import time
 
 import numpy as np
 
+XOFF = 2   # position of cell 0 in a padded row (uniform_device.cuh)
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -38,9 +39,7 @@ def build(force=False):
     cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
            "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC, '-DMMF_EMU_PTX_HELPERS="emu_ptx_helpers.h"',
            "-o", LIB, os.path.join(HERE, "emu_stage.cpp")]
-    if os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        cmd.insert(1, "-DMMF_EMU_HAVE_V6")
-    # kernel build options under test, e.g. MMF_EMU_CXXFLAGS="-DMMF_V6_EARLY_RCP=1" (use with MMF_EMU_LIB=<other file>)
+    # kernel build options under test, e.g. MMF_EMU_CXXFLAGS="-DMMF_R_UNROLL=1" (use with MMF_EMU_LIB=<other file>)
     cmd[1:1] = os.environ.get("MMF_EMU_CXXFLAGS", "").split()
     subprocess.run(cmd, check=True)
 
@@ -75,7 +74,7 @@ def load():
 
 def tile_rows(form, nw):
     """y rows a CTA of nw warps updates (StageShape::rows in uniform_launch.cuh)."""
-    return 2 * (nw - 1) if form == "w" else nw - 1 if form == "h" else nw - 2   # 'b': the rotate-form geometry
+    return nw - 2
 
 
 def ia(v):
@@ -93,7 +92,7 @@ class Box:
         lib.emu_padded(self.dims.ctypes.data_as(_I), pad.ctypes.data_as(_I), C.byref(fs))
         self.pad, self.fs = pad, fs.value
         self.ijk = m["cell_ijk"].astype(np.int64)
-        self.off = ((self.ijk[:, 2] + 1) * pad[1] + self.ijk[:, 1] + 1) * pad[0] + self.ijk[:, 0] + 1
+        self.off = ((self.ijk[:, 2] + 1) * pad[1] + self.ijk[:, 1] + 1) * pad[0] + self.ijk[:, 0] + XOFF
         # one BC code per side, from the border interfaces of the host description
         self.bc = [-9] * 6
         for f in np.nonzero(m["neigh"] < 0)[0]:
@@ -112,10 +111,10 @@ class Box:
             inner = np.zeros((nz, ny, nx), np.uint8)
             inner[self.ijk[:, 2], self.ijk[:, 1], self.ijk[:, 0]] = 1 - m["solved"].astype(np.uint8)
             vol = np.zeros((pz, py, px), np.uint8)
-            vol[1:nz + 1, 1:ny + 1, 1:nx + 1] = inner
+            vol[1:nz + 1, 1:ny + 1, XOFF:nx + XOFF] = inner
             vol[0, :, :] = vol[1, :, :]; vol[nz + 1, :, :] = vol[nz, :, :]
             vol[:, 0, :] = vol[:, 1, :]; vol[:, ny + 1, :] = vol[:, ny, :]
-            vol[:, :, 0] = vol[:, :, 1]; vol[:, :, nx + 1] = vol[:, :, nx]
+            vol[:, :, XOFF - 1] = vol[:, :, XOFF]; vol[:, :, nx + XOFF] = vol[:, :, nx + XOFF - 1]
             self.solid = np.zeros(self.fs, np.uint8)
             self.solid[:px * py * pz] = vol.reshape(-1)
             # kernel form 'c': fluid cells with a wall interface get flag 2 and are listed by padded offset
@@ -169,8 +168,8 @@ class Box:
                     c[(axis + 1) % 3], c[(axis + 2) % 3] = a, b
                     gcell = list(c)
                     gcell[axis] = ext[axis] if hi else -1
-                    oc = ((c[2] + 1) * py + c[1] + 1) * px + c[0] + 1
-                    og = ((gcell[2] + 1) * py + gcell[1] + 1) * px + gcell[0] + 1
+                    oc = ((c[2] + 1) * py + c[1] + 1) * px + c[0] + XOFF
+                    og = ((gcell[2] + 1) * py + gcell[1] + 1) * px + gcell[0] + XOFF
                     cons = np.ascontiguousarray(arr[:, oc])
                     out = np.empty(5)
                     self.oracle.lib.orc_eval_interface_bc_values(prob, bc, point.ctypes.data_as(_D), n.ctypes.data_as(_D),
@@ -189,17 +188,17 @@ class Box:
         lo[:] = np.array([1.0, 0.0, 0.0, 0.0, 2.5])[:, None]
         hi[:] = lo
         vol = arr[:, :px * py * pz].reshape(5, pz, py, px)
-        lo[:, :pitch * (nz + 2)] = vol[:, :, :, 0].reshape(5, -1)
-        hi[:, :pitch * (nz + 2)] = vol[:, :, :, nx + 1].reshape(5, -1)
-        vol[:, :, :, 0] = np.nan
-        vol[:, :, :, nx + 1] = np.nan
+        lo[:, :pitch * (nz + 2)] = vol[:, :, :, XOFF - 1].reshape(5, -1)
+        hi[:, :pitch * (nz + 2)] = vol[:, :, :, nx + XOFF].reshape(5, -1)
+        vol[:, :, :, XOFF - 1] = np.nan
+        vol[:, :, :, nx + XOFF] = np.nan
         return lo, hi, fs, pitch
 
     def smem_doubles(self, form, nw):
-        if form in ("d", "h", "w"):
-            nr = nw + (1 if form in ("h", "w") else 0)   # merged halo: one more (virtual) row
-            return nr * 2 * 16 * 32 + 4 * nr      # double-buffered records and fluxes, two mbarriers per slot and row
-        return nw * 16 * 32 + 2 * nw
+        base = nw * 16 * 32 + 2 * nw                 # records and fluxes, two mbarriers per row
+        if form == "m":                              # + the staging rows of the bulk tensor stores (stage_ts_smem_bytes)
+            return (base * 8 + 127) // 128 * 16 + (nw - 2) * 2 * 160
+        return base
 
     def eig_body(self, arr):
         """uniform_eig_body_kernel: the max eigenvalue that chooses dt on a box with bodies."""
@@ -215,8 +214,8 @@ class Box:
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
         dirichlet = np.zeros(5)
-        if (self.solid is not None) != (form in ("b", "c")):
-            raise RuntimeError("kernel forms 'b' and 'c' are the ones for a box with bodies, and only those")
+        if (self.solid is not None) != (form == "c"):
+            raise RuntimeError("kernel form 'c' is the one for a box with bodies, and only that one")
         flags = self.flag_c if form == "c" else self.solid
         self.lib.emu_set_solid(flags.ctypes.data if flags is not None else None)
         e_wall, compact = 0.0, None
@@ -310,7 +309,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="p,r,d,h,w,b,c")
+    ap.add_argument("--forms", default="r,m,c")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -320,8 +319,6 @@ def main():
     lib = load()
     oracle = oracle_lib.load()
     forms = [f for f in args.forms.split(",") if f]
-    if not os.path.exists(os.path.join(CSRC, "uniform_stage_v6.cuh")):
-        forms = [f for f in forms if f not in ("d", "h", "w", "b", "c")]
     cases = []
     m = oracle.problem_mesh("vortex_xy", 3, 16)
     cases.append(("vortex 16^3 morton", m, 0, 6))
@@ -334,9 +331,9 @@ def main():
     # boxes with bodies (kernel form 'b' only): a box body off the Morton cube's centre, two bodies touching
     # the border, a one-cell body
     body_cases = []
-    body_forms = [f for f in forms if f in ("b", "c")]
+    body_forms = [f for f in forms if f == "c"]
     if body_forms:
-        forms = [f for f in forms if f not in ("b", "c")]
+        forms = [f for f in forms if f != "c"]
         body_cases.append(("radsod 16^3 + box body", oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]]), 0, 6))
         if not args.quick:
             body_cases.append(("sod3d_x 16^3 + 2 bodies at the border", oracle.problem_mesh(

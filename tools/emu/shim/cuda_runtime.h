@@ -32,6 +32,8 @@
 #define __shared__
 #define __launch_bounds__(...)
 #define __maxnreg__(...)
+#define __align__(n)
+#define __grid_constant__
 
 namespace emu {
 

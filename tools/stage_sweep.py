@@ -30,20 +30,30 @@ def run_one(var, size, steps):
     import hashlib
     U, h = vortex(size)
     cells = size ** 3
-    cfg, lz = var.split("@") if "@" in var else (var, "0")   # e.g. p16:p16:r12:r12@43
+    cfg, lz = var.split("@") if "@" in var else (var, "0")   # e.g. r16:r16:r12:r12@43
     os.environ["MMF_STAGE_CFG"] = cfg
     if int(lz) > 0:
         os.environ["MMF_STAGE_LZ"] = lz
     else:
         os.environ.pop("MMF_STAGE_LZ", None)
+    # MMF_SWEEP_TOLERANT=1: experiment builds whose results are wrong on purpose (e.g. -DMMF_EXP_NOSYNC=1) trip the
+    # library's internal eigenvalue check at the end of mmf_run; the launches have run and are timed all the same
+    tolerant = os.environ.get("MMF_SWEEP_TOLERANT", "0") not in ("", "0")
+
+    def run(sol, n):
+        try:
+            sol.run(0.45, h, 0.0, 1e30, max_steps=n)
+        except mmf.MmfError:
+            if not tolerant:
+                raise
     with mmf.EulerSolver.uniform((size,) * 3, h, [0] * 6, cell_numbering=mmf.NUMBERING_LEXICOGRAPHIC) as s:
         s.set_state(mmf.FIELD_U, U)
-        s.run(0.45, h, 0.0, 1e30, max_steps=3)
+        run(s, 3)
         s.timer_start()
-        s.run(0.45, h, 0.0, 1e30, max_steps=steps)
+        run(s, steps)
         ms = s.timer_stop()
         s.profile_begin()
-        s.run(0.45, h, 0.0, 1e30, max_steps=steps)
+        run(s, steps)
         kms, kn = s.profile_end()
         out = s.get_state(mmf.FIELD_U)
     st = [kms[i] / max(kn[i], 1) for i in (1, 2, 3)]
@@ -78,7 +88,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--variants", default="p16:p16:r12:r12,p16:p16:d12:d12,p16:p16:h12:h12,p16:h16:h12:h12,p16:p16:w8:w8,p16:w8:w8:w8,w8,h12,h16,d12,d16,p12,r12,p16,r16,312")
+    ap.add_argument("--variants", default="r12,m12,r16,r8,r16:r16:r12:r12")
     ap.add_argument("--variant-timeout", type=float, default=90.0,
                     help="seconds per variant: every variant runs in its own process, so a kernel form that hangs on real "
                          "hardware costs its own slot only")
