@@ -1,9 +1,9 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<r|c|m> -DMMF_TU_FORM_ID=<0|1|2> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<r|c|t> -DMMF_TU_FORM_ID=<0|1|2> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 //   r = the rotate form (uniform_stage_v5r.cuh), the default of every stage
 //   c = the rotate form for a box with bodies (uniform_stage_v5rb.cuh), wall cells by a small pass around it
-//   m = the rotate form with bulk tensor (TMA) stores (uniform_stage_v5r.cuh, TS), opt-in
+//   t = the same scheme with its input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh)
 #include "uniform_launch.cuh"
 
 #ifndef MMF_TU_FORM_ID // a bare `nvcc -c stage_tu.cu` (no Makefile): the rotate form, RHS only
@@ -12,12 +12,15 @@
 #define MMF_TU_STAGE 0
 #endif
 
-#if MMF_TU_FORM_ID == 0 || MMF_TU_FORM_ID == 2
+#if MMF_TU_FORM_ID == 0
 #include "uniform_stage_v5r.cuh"
 #elif MMF_TU_FORM_ID == 1
 #include "uniform_stage_v5rb.cuh"
+#elif MMF_TU_FORM_ID == 2
+#include "uniform_stage_v5r.cuh"
+#include "uniform_stage_t.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (r), 1 (c) or 2 (m)"
+#error "MMF_TU_FORM_ID must be 0 (r), 1 (c) or 2 (t)"
 #endif
 
 namespace mmf {
@@ -44,11 +47,16 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     }
     return MMF_OK;
 #elif MMF_TU_FORM_ID == 2
-    (void) sh;
-    // 12 warps, bulk tensor stores
-    if (uniform_use_xghost(ctx))
-        return launch_stage_ts(ctx, uniform_stage_kernel_v5m<STAGE, ORDER, 12, true>, STAGE, 12, stage_ts_smem_bytes(12), Sin, Un, Out, d_max);
-    return launch_stage_ts(ctx, uniform_stage_kernel_v5m<STAGE, ORDER, 12, false>, STAGE, 12, stage_ts_smem_bytes(12), Sin, Un, Out, d_max);
+    // compact x ghost columns (an x partition side) are only read by the rotate form
+    if (uniform_use_xghost(ctx)) {
+        if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16, true>, STAGE, 16, stage_v5_smem_bytes(16), Sin, Un, Out, d_max);
+        return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>, STAGE, 12, stage_v5_smem_bytes(12), Sin, Un, Out, d_max);
+    }
+#define MMF_LAUNCH_T(NWV, DV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV>, STAGE, NWV, stage_t_smem_bytes(NWV, STAGE, DV), Sin, Un, Out, d_max)
+    if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH);
+    if (sh.nw == 8) MMF_LAUNCH_T(8, T_DEPTH);
+    MMF_LAUNCH_T(12, T_DEPTH);
+#undef MMF_LAUNCH_T
 #else
     const bool xgk = uniform_use_xghost(ctx);
     // record (11) + flux (5) doubles per lane and row, two mbarriers per row

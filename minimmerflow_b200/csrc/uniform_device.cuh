@@ -60,10 +60,10 @@ struct XGhost {
 // kernel runs, and a non-coherent L1 line fetched earlier on the same SM could hold the old values
 __device__ __forceinline__ double ldsin(const double *p) { return __ldcg(p); }
 
-// Position of cell 0 in a padded row.  Two, not one: a row then reads [pad][ghost][cells 0 .. nx-1][ghost][pad ...]
-// and cell 0 sits on a 16-byte boundary (rows are multiples of 32 bytes), which is what a bulk tensor (TMA) store
-// needs for the start of a box of 8-byte elements; the x windows of the stage kernels start at even cells.
-constexpr int XOFF = 2;
+// Position of cell 0 in a padded row: the x ghost sits at column 0.  The x windows of the stage kernels start at
+// cell bx*XW - 1 with XW even, i.e. at an even padded column, and rows are multiples of 32 bytes: the first byte of
+// every box row a bulk tensor (TMA) load fetches lies on a 16-byte boundary, which the hardware demands.
+constexpr int XOFF = 1;
 __host__ __device__ constexpr int padded_row(int nx) { return (nx + XOFF + 1 + 3) / 4 * 4; }
 
 __host__ __device__ __forceinline__ long long uoff(const UniformGeom &g, int i, int j, int k)

@@ -15,7 +15,7 @@ namespace mmf {
 
 // which stage-kernel form runs a stage and with how many warps per CTA:
 //   'r' the rotate form of the low-face streaming kernel (uniform_stage_v5r.cuh), the default: 12 warps
-//   'm' the same with bulk tensor (TMA) stores of the output (opt-in: measured 6 % slower, see there)
+//   't' the same scheme with the input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh)
 //   'c' the rotate form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never
 //       by MMF_STAGE_CFG), the wall cells recomputed by a small pass around the stage kernel
 struct StageShape {
@@ -39,9 +39,9 @@ struct UniformPath {
     float *cta_est = nullptr;         // per stage-3 tile: FP32 estimate of the max eigenvalue of what it wrote
     int *eig_cand = nullptr;          // [0] = number of listed tiles, then their indices
     int n_tiles3 = 0;
-    // kernel form 'm': bulk tensor stores; one descriptor per state array (U, Wa, Wb, RHS), built with the array
-    TmaDesc out_map[4];
-    bool out_map_ok[4] = { false, false, false, false };
+    // kernel form 't': bulk tensor loads; descriptors of the padded arrays per (array, rows of the box)
+    struct InMap { const double *arr; int rows; TmaDesc map; };
+    std::vector<InMap> in_maps;
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
     bool clamp_ff = true;             // free-flow ghosts are never read by the stage kernels (LoadClamp)
     // bodies: one flag per padded cell, 1 = not solved (src/main.cpp:221-237), 2 = fluid cell with a wall interface,
@@ -122,133 +122,133 @@ static cudaError_t stage_smem_attribute(K kern, size_t smem)
     return e;
 }
 
-template <typename K>
-static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
-                          double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const UniformGeom &g = u->g;
-    const int lz = u->shape[stage].lz, rows = u->shape[stage].rows();
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
-    for (int q = 0; q < 3; ++q) {
-        if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
-            MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
-            u->push_pending[q] = false;
-        }
-    }
+// what every launch of a stage kernel starts with: the grid, the wait for a push that still reads the output array,
+// the in-kernel halo wait of a partitioned run and the compact x ghost columns
+struct StageLaunchArgs {
+    dim3 grid;
     HaloWait hw{};
-    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
-    if (ctx->comm && u->p2p && u->halo_inkernel) {
-        int a = -1;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
-        for (int s = 0; s < 6; ++s) hw.mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
-        if (a >= 0 && hw.mask) {
-            hw.flags = u->flags;
-            hw.seq = u->arr_seq[a];
-            hw.tile_order = u->tile_order[stage];
-            if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
-        }
-    }
     XGhost xg{};
-    if (hw.flags && uniform_use_xghost(ctx)) { // x ghosts of partition sides come from the compact columns
-        int a = 0;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) a = q;
-        xg.fs = u->xg_fs;
-        xg.pitch = g.ny + 2;
-        if (u->nbr_rank[0] >= 0) xg.lo = u->xghost + (size_t) (0 * 3 + a) * NF * u->xg_fs;
-        if (u->nbr_rank[1] >= 0) xg.hi = u->xghost + (size_t) (1 * 3 + a) * NF * u->xg_fs;
-    }
-    {
-        ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u), hw, xg);
-    }
-    MMF_LAUNCH_CHECK(ctx);
-    return MMF_OK;
-}
+};
 
-// ---- bulk tensor stores (kernel form 'm') ------------------------------------------------------------------------
-// The descriptor of one padded state array for STORES: dimensions (x, y, z, field) = (nx, ny, nz, NF) with element
-// (0, 0, 0, f) at cell (0, 0, 0) of field f -- 16-byte aligned because cell 0 sits at column XOFF = 2 of a padded row,
-// and every x window starts at an even cell, which the start of a box of 8-byte elements needs -- and a box of
-// XW x 1 x 1 x NF: everything a ragged tile writes beyond the box of cells is clipped by the hardware.  cuTensorMapEncodeTiled comes from the driver through the runtime
-// (cudaGetDriverEntryPoint): the library does not link libcuda.
-static int uniform_make_out_map(mmf_ctx *ctx, double *arr, TmaDesc *map)
-{
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        MMF_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
-    const UniformGeom &g = ctx->uni->g;
-    static_assert(XOFF % 2 == 0 && XW % 2 == 0, "bulk tensor stores of doubles start at even columns");
-    const cuuint64_t dims[4] = { (cuuint64_t) g.nx, (cuuint64_t) g.ny, (cuuint64_t) g.nz, (cuuint64_t) NF };
-    const cuuint64_t strides[3] = { (cuuint64_t) g.px * 8, (cuuint64_t) g.px * g.py * 8, (cuuint64_t) g.fs * 8 }; // bytes, dims 1..3
-    const cuuint32_t box[4] = { (cuuint32_t) XW, 1, 1, (cuuint32_t) NF };
-    const cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    void *base = arr + uoff(g, 0, 0, 0);
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d box", (int) r, g.nx, g.ny, g.nz);
-    return MMF_OK;
-}
-
-// launch_stage_k for the kernels that take the output's tensor descriptor as their last argument
-template <typename K>
-static int launch_stage_ts(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
-                           double *d_max)
+static int stage_launch_prelude(mmf_ctx *ctx, int stage, const double *Sin, double *Out, StageLaunchArgs &a)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    int a = -1;
-    for (int q = 0; q < 4; ++q) if (Out == u->arr[q]) a = q;
-    if (a < 0) return fail(ctx, MMF_ERR_INVALID, "bulk tensor stores: the output is not one of the state arrays");
-    if (!u->out_map_ok[a]) {
-        if (int rc = uniform_make_out_map(ctx, u->arr[a], &u->out_map[a])) return rc;
-        u->out_map_ok[a] = true;
-    }
     const int lz = u->shape[stage].lz, rows = u->shape[stage].rows();
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
+    a.grid = dim3((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
     for (int q = 0; q < 3; ++q) {
         if (Out == u->arr[q] && u->push_pending[q]) { // the array about to be overwritten is still being pushed
             MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, u->ev_push[q], 0));
             u->push_pending[q] = false;
         }
     }
-    HaloWait hw{};
-    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
+    HaloWait &hw = a.hw;
+    hw.tx = (int) a.grid.x; hw.ty = (int) a.grid.y; hw.tz = (int) a.grid.z;
+    int ain = -1;
+    for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) ain = q;
     if (ctx->comm && u->p2p && u->halo_inkernel) {
-        int ain = -1;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) ain = q;
         for (int s = 0; s < 6; ++s) hw.mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
         if (ain >= 0 && hw.mask) {
             hw.flags = u->flags;
             hw.seq = u->arr_seq[ain];
             hw.tile_order = u->tile_order[stage];
-            if (hw.tile_order) grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+            if (hw.tile_order) a.grid = dim3(a.grid.x * a.grid.y * a.grid.z, 1, 1);
         }
     }
-    XGhost xg{};
     if (hw.flags && uniform_use_xghost(ctx)) { // x ghosts of partition sides come from the compact columns
-        int ain = 0;
-        for (int q = 0; q < 3; ++q) if (Sin == u->arr[q]) ain = q;
-        xg.fs = u->xg_fs;
-        xg.pitch = g.ny + 2;
-        if (u->nbr_rank[0] >= 0) xg.lo = u->xghost + (size_t) (0 * 3 + ain) * NF * u->xg_fs;
-        if (u->nbr_rank[1] >= 0) xg.hi = u->xghost + (size_t) (1 * 3 + ain) * NF * u->xg_fs;
+        const int q = ain < 0 ? 0 : ain;
+        a.xg.fs = u->xg_fs;
+        a.xg.pitch = g.ny + 2;
+        if (u->nbr_rank[0] >= 0) a.xg.lo = u->xghost + (size_t) (0 * 3 + q) * NF * u->xg_fs;
+        if (u->nbr_rank[1] >= 0) a.xg.hi = u->xghost + (size_t) (1 * 3 + q) * NF * u->xg_fs;
     }
+    return MMF_OK;
+}
+
+template <typename K>
+static int launch_stage_k(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
+                          double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    StageLaunchArgs a;
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
+    if (int rc = stage_launch_prelude(ctx, stage, Sin, Out, a)) return rc;
     {
         ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u), hw, xg, u->out_map[a]);
+        kern<<<a.grid, nw * 32, smem, ctx->stream>>>(u->g, Sin, Un, Out, ctx->d_ctl, d_max, u->shape[stage].lz,
+                                                     (stage == 3) ? u->cta_est : nullptr, uniform_load_clamp(u), a.hw, a.xg);
+    }
+    MMF_LAUNCH_CHECK(ctx);
+    return MMF_OK;
+}
+
+// ---- bulk tensor loads (kernel form 't') -------------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver through the runtime (cudaGetDriverEntryPoint): the library does not
+// link libcuda.
+typedef CUresult (*TmaEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int uniform_tma_encoder(mmf_ctx *ctx, TmaEncodeFn *out)
+{
+    static TmaEncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MMF_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<TmaEncodeFn>(fn);
+    }
+    *out = encode;
+    return MMF_OK;
+}
+
+// The descriptor of one padded state array for LOADS: dimensions (x, y, z, field) = (px, py, pz, NF), i.e. the whole
+// padded array with its ghost shell, element (0, 0, 0, f) = the first padded element of field f (cudaMalloc alignment;
+// rows are multiples of 32 bytes, field strides of 128), and a box of 32 x `rows` x 1 x NF: one z plane of everything
+// a CTA of the stage kernel reads.  Box coordinates are element coordinates and need no alignment; what sticks out
+// of the array is zero filled.  Descriptors are cached per (array, rows).
+static int uniform_in_map(mmf_ctx *ctx, const double *arr, int rows, const TmaDesc **out)
+{
+    UniformPath *u = ctx->uni;
+    for (const auto &m : u->in_maps) if (m.arr == arr && m.rows == rows) { *out = &m.map; return MMF_OK; }
+    TmaEncodeFn encode = nullptr;
+    if (int rc = uniform_tma_encoder(ctx, &encode)) return rc;
+    const UniformGeom &g = u->g;
+    const cuuint64_t dims[4] = { (cuuint64_t) g.px, (cuuint64_t) g.py, (cuuint64_t) g.pz, (cuuint64_t) NF };
+    const cuuint64_t strides[3] = { (cuuint64_t) g.px * 8, (cuuint64_t) g.px * g.py * 8, (cuuint64_t) g.fs * 8 };
+    const cuuint32_t box[4] = { 32, (cuuint32_t) rows, 1, (cuuint32_t) NF };
+    const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    UniformPath::InMap m;
+    m.arr = arr;
+    m.rows = rows;
+    const CUresult r = encode(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(arr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for loads of a %d x %d x %d box", (int) r, g.nx, g.ny, g.nz);
+    u->in_maps.push_back(m);
+    *out = &u->in_maps.back().map;
+    return MMF_OK;
+}
+
+template <typename K>
+static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
+                           double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    const TmaDesc *smap = nullptr, *umap = nullptr;
+    if (int rc = uniform_in_map(ctx, Sin, nw, &smap)) return rc;
+    const TmaDesc sm = *smap; // (the cache may grow below)
+    if (stage >= 2) { if (int rc = uniform_in_map(ctx, Un, nw - 2, &umap)) return rc; }
+    const TmaDesc um = umap ? *umap : sm;
+    StageLaunchArgs a;
+    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
+    if (int rc = stage_launch_prelude(ctx, stage, Sin, Out, a)) return rc;
+    if (a.xg.lo || a.xg.hi) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 't' does not read compact x ghost columns");
+    {
+        ScopedLaunchTimer timer(ctx, stage);
+        kern<<<a.grid, nw * 32, smem, ctx->stream>>>(u->g, Out, ctx->d_ctl, d_max, u->shape[stage].lz,
+                                                     (stage == 3) ? u->cta_est : nullptr, uniform_load_clamp(u), a.hw, sm, um);
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -289,18 +289,18 @@ typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const d
     int MMF_STAGE_TU_NAME(F, 3)(mmf_ctx *, int, const double *, const double *, double *, double *);
 MMF_DECLARE_STAGE_TUS(r)  // uniform_stage_v5r.cuh
 MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies
-MMF_DECLARE_STAGE_TUS(m)  // uniform_stage_v5r.cuh with bulk tensor stores
+MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_t.cuh: input staged by bulk tensor loads
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('r', 'c', 'm') for a stage
+// the launcher of a kernel form ('r', 'c', 't') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
     static const StageLauncher tab[3][4] = {
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
         { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
-        { launch_stage_m_0, launch_stage_m_1, launch_stage_m_2, launch_stage_m_3 },
+        { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
     };
-    return tab[(form == 'c') ? 1 : (form == 'm') ? 2 : 0][stage];
+    return tab[(form == 'c') ? 1 : (form == 't') ? 2 : 0][stage];
 }
 
 } // namespace mmf

@@ -120,10 +120,11 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         fill_benign_kernel<<<grid_for(g.fs, 256), 256, 0, ctx->stream>>>(u->arr[a], g.fs);
         MMF_LAUNCH_CHECK(ctx);
     }
-    // Launch shapes, measured at 256^3 on B200 (profiles/r02c_experiments.md): the rotate form at 12 warps (158-166
-    // registers, no spills) is the fastest kernel of every stage.  MMF_STAGE_CFG overrides per stage, e.g.
-    // "r12:r16:m12:m12" (stage 0:1:2:3; 'm' = the same kernel with bulk tensor stores, 12 warps).
-    for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'r', 12 };
+    // Launch shapes, measured at 256^3 on B200 (profiles/r02d_experiments.md): the form whose input is staged by bulk
+    // tensor loads, at 16 warps (128 registers), is the fastest kernel of every stage.  MMF_STAGE_CFG overrides per
+    // stage, e.g. "r12:t16:t12:t12" (stage 0:1:2:3; 'r' = the rotate form with per-thread global loads, which is
+    // also what runs when an x side is a partition side).
+    for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 't', 16 };
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
         int st = 0;
         for (const char *p = cfg; *p && st < 4;) {
@@ -133,8 +134,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'r' && sh.form != 'm') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
-            if (sh.form == 'm') sh.nw = 12;
+            if ((sh.form != 'r' && sh.form != 't') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }

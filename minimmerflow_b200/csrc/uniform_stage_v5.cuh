@@ -28,7 +28,11 @@ namespace mmf {
 __device__ __forceinline__ void mbar_arrive_elect(unsigned long long *bar, int lane)
 {
     __syncwarp();
+#if MMF_ARRIVE_PRED
+    mbar_arrive_if(bar, lane == 0); // one predicated instruction: no branch, the warp stays converged for the compiler
+#else
     if (lane == 0) mbar_arrive(bar);
+#endif
 }
 
 // interface-order key of a cell's low face along `axis`: Morton 3*ctz(coord)+axis (the creator of

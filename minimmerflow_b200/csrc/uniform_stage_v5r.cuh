@@ -19,54 +19,18 @@ namespace mmf {
 #endif
 constexpr int R_UNROLL = MMF_R_UNROLL;
 
-// ---- TS: the output leaves through shared memory and one bulk tensor store per warp and plane -------------------
-// (ptx_helpers.cuh: tma_store_4d).  Staging: per update row two slots of NF x XW doubles (the dense box of the
-// tensor map), padded to a multiple of 128 bytes, behind the exchange buffers and barriers.
-constexpr int TS_SLOT_DOUBLES = (NF * XW * 8 + 127) / 128 * 128 / 8;
 __host__ __device__ constexpr size_t stage_v5_smem_bytes(int nw)
 {
     return (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
 }
-__host__ __device__ constexpr size_t stage_ts_offset_bytes(int nw) { return (stage_v5_smem_bytes(nw) + 127) / 128 * 128; }
-__host__ __device__ constexpr size_t stage_ts_smem_bytes(int nw)
-{
-    return stage_ts_offset_bytes(nw) + (size_t) (nw - 2) * 2 * TS_SLOT_DOUBLES * sizeof(double);
-}
 
-// finish_plane with the result into this lane's place of a staging slot instead of global memory
-template <int STAGE>
-__device__ __forceinline__ void finish_plane_ts(const double *S, const double *AFz, const double *pU, const double *pUn,
-                                                double dt, double volume, double y_vol, double *slot_lane, bool lane_ok,
-                                                bool pred, float &est_max)
-{
-    double out[NF];
-#pragma unroll
-    for (int k = 0; k < NF; ++k) {
-        const double rhs = S[k] - AFz[k];
-        if (STAGE == 0) {
-            out[k] = rhs;
-        } else {
-            const double dq = div_nr(dt * rhs, volume, y_vol); // dt * RHS[k] / cellVolume
-            if (STAGE == 1)      out[k] = pU[k] + dq;
-            else if (STAGE == 2) out[k] = 0.75 * pUn[k] + 0.25 * (pU[k] + dq);
-            else                 out[k] = (1. / 3) * pUn[k] + (2. / 3) * (pU[k] + dq);
-        }
-        if (lane_ok) slot_lane[k * XW] = out[k];
-    }
-    if (STAGE == 3) {
-        const float est = eig_estimate(out);
-        est_max = fmaxf(est_max, pred ? est : 0.f); // fmaxf drops a NaN from a never-stored halo lane
-    }
-}
-
-template <int STAGE, int ORDER, int NW, bool XG, bool TS>
+template <int STAGE, int ORDER, int NW, bool XG>
 __device__ __forceinline__ void
 stage_v5r_body(const UniformGeom &g, const double *__restrict__ Sin, const double *Un, double *Out,
                const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-               float *__restrict__ cta_est, const LoadClamp &lc, const HaloWait &hw, const XGhost &xg, const TmaDesc *omap)
+               float *__restrict__ cta_est, const LoadClamp &lc, const HaloWait &hw, const XGhost &xg)
 {
-    extern __shared__ double smem[]; // (no static shared memory in these kernels: the dynamic window starts 1 KB aligned,
-                                     //  which the staging rows of the bulk stores rely on: 128 bytes)
+    extern __shared__ double smem[];
     // sm_d[row][q][lane], q = U0..U4, Fy0..Fy4, lam_y ; sm_f[row][k][lane] = area * flux of (j-1 | j)
     double *sm_d = smem;
     double *sm_f = smem + NW * 11 * 32;
@@ -198,8 +162,6 @@ stage_v5r_body(const UniformGeom &g, const double *__restrict__ Sin, const doubl
         const double *d_dn = sm_d + (row - (MMF_EXP_NOSYNC ? 0 : 1)) * 11 * 32 + lane;
         double *f_own = sm_f + row * NF * 32 + lane;
         const double *f_up = sm_f + (row + (MMF_EXP_NOSYNC ? 0 : 1)) * NF * 32 + lane;
-        double *ts_row = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + stage_ts_offset_bytes(NW)) +
-                         (row - 1) * 2 * TS_SLOT_DOUBLES; // (TS only)
 
         const double *sp  = scol + (long long) (max(z0 - 1, lc.klo) + 1) * splane; // plane z0-1 (clamped)
         const double *unp = Un + col + (long long) (z0 + 1) * splane; // plane z0
@@ -255,22 +217,8 @@ stage_v5r_body(const UniformGeom &g, const double *__restrict__ Sin, const doubl
                 const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
                 lmz = (lam < lmz) ? lmz : lam;
             }
-            if (TS) {
-                double *slot = ts_row + ((kz - z0) & 1) * TS_SLOT_DOUBLES;
-                if (lane == 0) tma_store_wait_read<1>(); // the store that read this slot two planes ago is done with it
-                __syncwarp();
-                finish_plane_ts<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, slot + lane - 1, lane >= 1 && lane <= XW,
-                                       upd && kz > z0, est_max);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && in_y && kz > z0) { // plane kz-1 of row j, cells tid.bx*XW .. +XW-1 (clipped at the box)
-                    tma_store_4d(omap, slot, tid.bx * XW, j, kz - 1, 0);
-                    tma_store_commit();
-                }
-            } else {
-                finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
-                op += plane;
-            }
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && kz > z0, est_max);
+            op += plane;
 
             // ---- x interface (i-1 | i): lane-1's state by warp shuffle ---------------------------------
             double AFx[NF];
@@ -373,22 +321,7 @@ stage_v5r_body(const UniformGeom &g, const double *__restrict__ Sin, const doubl
             axis_flux<2>(q, cFz, clz);
             const double lam = llf_area_flux(pU, pFz, plz, nxt, cFz, clz, Ah, AFz);
             lmz = (lam < lmz) ? lmz : lam;
-            if (TS) {
-                double *slot = ts_row + ((z1 - z0) & 1) * TS_SLOT_DOUBLES;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-                finish_plane_ts<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, slot + lane - 1, lane >= 1 && lane <= XW,
-                                       upd, est_max);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && in_y) {
-                    tma_store_4d(omap, slot, tid.bx * XW, j, z1 - 1, 0);
-                    tma_store_commit();
-                }
-                if (lane == 0) tma_store_wait_read<0>(); // the staging rows must outlive the reads of the last stores
-            } else {
-                finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
-            }
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
         }
         lmax = xf_ok ? lmx : 0.0;
         if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;
@@ -405,18 +338,7 @@ uniform_stage_kernel_v5r(const UniformGeom g, const double *__restrict__ Sin, co
                          const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
                          float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw, const XGhost xg)
 {
-    stage_v5r_body<STAGE, ORDER, NW, XG, false>(g, Sin, Un, Out, ctl, max_eig, lz, cta_est, lc, hw, xg, nullptr);
-}
-
-// kernel form 'm': the rotate form with bulk tensor stores (TS); omap describes the interior of the output array
-template <int STAGE, int ORDER, int NW, bool XG>
-__global__ void __maxnreg__(stage_regs(NW))
-uniform_stage_kernel_v5m(const UniformGeom g, const double *__restrict__ Sin, const double *Un, double *Out,
-                         const StepControl *__restrict__ ctl, double *__restrict__ max_eig, const int lz,
-                         float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw, const XGhost xg,
-                         const __grid_constant__ TmaDesc omap)
-{
-    stage_v5r_body<STAGE, ORDER, NW, XG, true>(g, Sin, Un, Out, ctl, max_eig, lz, cta_est, lc, hw, xg, &omap);
+    stage_v5r_body<STAGE, ORDER, NW, XG>(g, Sin, Un, Out, ctl, max_eig, lz, cta_est, lc, hw, xg);
 }
 
 } // namespace mmf

@@ -25,7 +25,7 @@ def emu():
     return run_emu.load()
 
 
-@pytest.mark.parametrize("form", ["r", "m"])
+@pytest.mark.parametrize("form", ["r", "t"])
 @pytest.mark.parametrize("chaos", [0, 300])
 def test_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, form, chaos):
     # Morton cube (the reference's numbering), z chunks of 6 planes: general and steady-state bodies
@@ -50,13 +50,13 @@ def test_emulated_mbarrier_keeps_ptx_phase_semantics(emu):
 
 def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
     """NUM_AXIS accumulation (x_lo - x_hi + y_lo - y_hi + z_lo - z_hi) is not the reference's order, so
-    there is no oracle for its bits; the bulk-store form must give exactly what the rotate form gives, and
+    there is no oracle for its bits; the form fed by bulk tensor loads must give exactly what the rotate form gives, and
     both stay within rounding of the oracle."""
     m = oracle.problem_mesh("radsod", 3, 16)
     U0 = oracle.init_state(m)
     ref, ref_eig = oracle.compute_rhs(m, U0)
     out = {}
-    for form in ("r", "m"):
+    for form in ("r", "t"):
         box = run_emu.Box(emu, oracle, dict(m), 2)
         U, R = box.new_array(), box.new_array()
         box.scatter(U, U0)
@@ -64,11 +64,11 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
         eig, _ = box.stage(form, 0, 8, 5, U, U, R, 0.0, 200, 5)
         assert eig == ref_eig
         out[form] = box.gather(R)
-    assert np.array_equal(out["r"], out["m"])
+    assert np.array_equal(out["r"], out["t"])
     assert np.abs(out["r"] - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("form", ["r", "m"])
+@pytest.mark.parametrize("form", ["r"])
 def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
     """Multi-GPU layout of an x partition side (XGhost): the halo lanes i = -1 / i = nx take their column
     from compact arrays [field][k+1][j+1] instead of the padded array.  Here the columns hold the
@@ -162,7 +162,7 @@ def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu,
 PLAIN_CASES_3D = [c for c in reference_cases() if c["dim"] == 3 and not c.get("bodies")]
 
 
-@pytest.mark.parametrize("form,nw", [("r", 12), ("r", 16), ("m", 12)])
+@pytest.mark.parametrize("form,nw", [("r", 12), ("t", 12), ("t", 16)])
 @pytest.mark.parametrize("case", PLAIN_CASES_3D, ids=lambda c: c["name"])
 def test_stage_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case, form, nw):
     """Every stage-kernel form through

@@ -43,39 +43,40 @@ inline void mbar_wait(unsigned long long *bar, unsigned parity)
 }
 
 #define MMF_EXP_NOSYNC 0
+#define MMF_ARRIVE_PRED 1
+inline void mbar_arrive_if(unsigned long long *bar, bool on) { if (on) mbar_arrive(bar); }
 
-// TMA stores: the descriptor is a plain struct here and the copy is synchronous (clipped at the tensor extents like
-// the hardware does); commit / wait / proxy fence have nothing left to do
+// TMA loads: the descriptor is a plain struct here and the copy is synchronous (what lies outside the tensor extents
+// is zero filled like the hardware does).  The producer's protocol is mbar_expect_tx -> tma_load_4d ... -> mbar_arrive:
+// with synchronous copies the announced byte count has nothing left to do and the one arrival completes the phase
+// after the data is in place, which is the ordering a consumer may rely on.
 struct TmaDesc {
-    double *base;            // element (0,0,0,0)
+    const double *base;      // element (0,0,0,0)
     long long stride[4];     // in elements
     int dim[4], box[4];
 };
-inline void fence_proxy_async_smem() {}
-inline void tma_store_4d(const TmaDesc *d, const void *smem_src, int c0, int c1, int c2, int c3)
+inline void fence_barrier_init() {}
+inline void fence_proxy_async_global() {}
+inline void mbar_expect_tx(unsigned long long *, unsigned) {}
+inline void tma_load_4d(const TmaDesc *d, void *smem_dst, unsigned long long *, int c0, int c1, int c2, int c3)
 {
     emu::chaos_delay();
-    const double *src = static_cast<const double *>(smem_src);
+    if ((c0 * 8) % 16) { fprintf(stderr, "emu: bulk tensor load from a box row that does not start on a 16-byte boundary\n"); abort(); }
+    double *dst = static_cast<double *>(smem_dst);
     const int c[4] = { c0, c1, c2, c3 };
     for (int q3 = 0; q3 < d->box[3]; ++q3)
         for (int q2 = 0; q2 < d->box[2]; ++q2)
             for (int q1 = 0; q1 < d->box[1]; ++q1)
                 for (int q0 = 0; q0 < d->box[0]; ++q0) {
                     const int x[4] = { c[0] + q0, c[1] + q1, c[2] + q2, c[3] + q3 };
-                    const double v = src[((q3 * d->box[2] + q2) * d->box[1] + q1) * d->box[0] + q0];
                     bool in = true;
                     for (int e = 0; e < 4; ++e) in = in && x[e] >= 0 && x[e] < d->dim[e];
-                    if (in) d->base[x[0] * d->stride[0] + x[1] * d->stride[1] + x[2] * d->stride[2] + x[3] * d->stride[3]] = v;
+                    dst[((q3 * d->box[2] + q2) * d->box[1] + q1) * d->box[0] + q0] =
+                        in ? d->base[x[0] * d->stride[0] + x[1] * d->stride[1] + x[2] * d->stride[2] + x[3] * d->stride[3]] : 0.0;
                 }
 }
-inline void tma_store_commit() {}
-template <int N> inline void tma_store_wait_read() {}
-
-template <int N> inline void reg_inc() {}   // register hand-over between warpgroups: nothing to emulate
-template <int N> inline void reg_dec() {}
 
 inline double rcp_nr(double b) { return 1.0 / b; }
-inline void rcp_nr2(double a, double b, double &ya, double &yb) { ya = 1.0 / a; yb = 1.0 / b; }
 inline double div_nr(double a, double b, double) { return a / b; }
 
 inline float rcp_approx_f32(float x) { return 1.0f / x; }

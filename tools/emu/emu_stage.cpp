@@ -4,6 +4,7 @@
 // standard headers that spell attributes the shim's CUDA keywords would rewrite come first
 #include <stdint.h>
 #include <stdio.h>
+#include <time.h>
 #include <string>
 #include <vector>
 
@@ -46,14 +47,24 @@ void yield_lane()
 
 void spin_pause(long long &spins, const char *what)
 {
+    // the watchdog is a wall-clock one: a warp that only keeps hand-shakes alive (kernel form 't': rows beyond the box)
+    // spins through a whole plane of its neighbours' arithmetic, however long the host takes for it
+    static thread_local struct timespec t0;
     ++spins;
     if ((spins & 63) == 0) sched_yield();
-    if (spins > g_spin_limit) {
-        Lane *me = tl_cur;
-        fprintf(stderr, "emu: HANG in %s: block (%u,%u,%u) warp %d lane %d gave up after %lld yields\n", what,
-                g_blockIdx.x, g_blockIdx.y, g_blockIdx.z, me->warp->index, me->lane, spins);
-        fflush(stderr);
-        _exit(3);
+    if (spins == 1) clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (spins > 100000) usleep(20);
+    if ((spins & 1023) == 0) {
+        struct timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double waited = (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+        if (waited > (double) g_spin_limit * 3e-6) { // the default limit of 2e7 "yields" = 60 s
+            Lane *me = tl_cur;
+            fprintf(stderr, "emu: HANG in %s: block (%u,%u,%u) warp %d lane %d gave up after %.0f s\n", what,
+                    g_blockIdx.x, g_blockIdx.y, g_blockIdx.z, me->warp->index, me->lane, waited);
+            fflush(stderr);
+            _exit(3);
+        }
     }
 }
 
@@ -168,6 +179,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 
 #include "uniform_stage_v5r.cuh"
 #include "uniform_stage_v5rb.cuh"
+#include "uniform_stage_t.cuh"
 #include "uniform_eligibility.h"
 #include "generic_kernels.cuh"
 #include "generic_tables.h"
@@ -190,14 +202,14 @@ struct Args {
     const unsigned char *solid; // form 'c': flag array of a box with bodies
 };
 
-// the emulated descriptor of the output array for the bulk tensor stores of form 'm' (uniform_make_out_map)
-static TmaDesc out_desc(const Args &a)
+// the emulated descriptor of a padded state array for the bulk tensor loads of form 't' (uniform_in_map)
+static TmaDesc in_desc(const Args &a, const double *arr, int rows)
 {
     TmaDesc d{};
-    d.base = a.Out + uoff(a.g, 0, 0, 0);
+    d.base = arr;
     d.stride[0] = 1; d.stride[1] = a.g.px; d.stride[2] = (long long) a.g.px * a.g.py; d.stride[3] = a.g.fs;
-    d.dim[0] = a.g.nx; d.dim[1] = a.g.ny; d.dim[2] = a.g.nz; d.dim[3] = NF;
-    d.box[0] = XW; d.box[1] = 1; d.box[2] = 1; d.box[3] = NF;
+    d.dim[0] = a.g.px; d.dim[1] = a.g.py; d.dim[2] = a.g.pz; d.dim[3] = NF;
+    d.box[0] = 32; d.box[1] = rows; d.box[2] = 1; d.box[3] = NF;
     return d;
 }
 
@@ -207,7 +219,6 @@ std::function<void()> bind_kernel_xg(int form, const Args &a)
 {
     switch (form) {
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'm': return [a] { uniform_stage_kernel_v5m<STAGE, ORDER, 12, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg, out_desc(a)); };
     default: return nullptr;
     }
 }
@@ -218,7 +229,7 @@ std::function<void()> bind_kernel(int form, const Args &a)
     if (a.xg.lo || a.xg.hi) return (NW == 12) ? bind_kernel_xg<STAGE, ORDER>(form, a) : nullptr;
     switch (form) {
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
-    case 'm': return [a] { uniform_stage_kernel_v5m<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg, out_desc(a)); };
+    case 't': return [a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW), in_desc(a, a.Un, NW - 2)); };
     case 'c': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
     default: return nullptr;
     }

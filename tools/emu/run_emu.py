@@ -5,7 +5,7 @@ hazards, buffer reuse races, index slips) before GPU time is spent on it.  Not a
 fallback, never timed; the GPU tests (tests/test_uniform_gpu.py) remain the parity proof.
 
     python tools/emu/run_emu.py                 # default matrix
-    python tools/emu/run_emu.py --forms r,m --nw 8,12 --chaos 300 --repeat 5
+    python tools/emu/run_emu.py --forms r,t --nw 8,12 --chaos 300 --repeat 5
 """
 import argparse
 import ctypes as C
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-XOFF = 2   # position of cell 0 in a padded row (uniform_device.cuh)
+XOFF = 1   # position of cell 0 in a padded row (uniform_device.cuh)
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -196,8 +196,9 @@ class Box:
 
     def smem_doubles(self, form, nw):
         base = nw * 16 * 32 + 2 * nw                 # records and fluxes, two mbarriers per row
-        if form == "m":                              # + the staging rows of the bulk tensor stores (stage_ts_smem_bytes)
-            return (base * 8 + 127) // 128 * 16 + (nw - 2) * 2 * 160
+        if form == "t":                              # the ring of bulk tensor loads + records, fluxes, mbarriers (stage_t_smem_bytes)
+            depth = 4
+            return depth * 5 * 32 * (2 * nw - 2) + nw * 11 * 32 + 2 * depth + 2 * nw
         return base
 
     def eig_body(self, arr):
@@ -309,7 +310,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="r,m,c")
+    ap.add_argument("--forms", default="r,t,c")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
