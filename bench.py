@@ -70,7 +70,7 @@ def vortex_state(dims, offset, global_n, length=10.0, origin=-5.0):
 def box_decomposition(n_ranks):
     """Process grid (px,py,pz) for N = 1,2,4,8 in the order a Morton partition of a cube splits:
     z first, then y, then x (x is the lowest Morton bit, src/main.cpp:159,183 + PABLO)."""
-    grid = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[n_ranks]
+    grid = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}[n_ranks]
     override = os.environ.get("MMF_BENCH_GRID")  # development: e.g. "2x1x1" to put the partition side on x
     if override:
         g = tuple(int(v) for v in override.split("x"))

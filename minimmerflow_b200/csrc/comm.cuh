@@ -336,6 +336,7 @@ __global__ void uniform_wait_kernel(const unsigned long long *flags, unsigned in
     __threadfence_system();
 }
 
+constexpr int DMA_SEQ_RING = 1024; // pinned sequence numbers the arrival counters are copied from (comm_uniform_dma_push)
 constexpr int IPC_HANDLES = 5; // U, Wa, Wb, arrival counters, compact x ghost columns
 constexpr size_t IPC_BLOB_BYTES = 512; // = MMF_IPC_BLOB_BYTES
 static_assert(IPC_HANDLES * sizeof(cudaIpcMemHandle_t) <= IPC_BLOB_BYTES, "IPC blob too small");
@@ -399,6 +400,11 @@ static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
         }
     }
     u->p2p = true;
+    // the copy engines carry the exchange when no x side is a partition side (MMF_DMA_PUSH=0: the push kernel)
+    u->dma_push = u->nbr_rank[0] < 0 && u->nbr_rank[1] < 0 && !(getenv("MMF_DMA_PUSH") && atoi(getenv("MMF_DMA_PUSH")) == 0);
+    if (u->dma_push && !u->seq_ring) {
+        MMF_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&u->seq_ring), DMA_SEQ_RING * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
     return uniform_build_tile_orders(ctx);
 }
 
@@ -406,10 +412,76 @@ static void comm_ipc_close(mmf_ctx *ctx)
 {
     UniformPath *u = ctx->uni;
     if (!u) return;
+    if (u->seq_ring) { cudaFreeHost(u->seq_ring); u->seq_ring = nullptr; }
+    u->dma_push = false;
     for (int s = 0; s < 6; ++s)
         for (int a = 0; a < IPC_HANDLES; ++a)
             if (u->ipc_opened[s][a]) { cudaIpcCloseMemHandle(u->ipc_opened[s][a]); u->ipc_opened[s][a] = nullptr; }
     u->p2p = false;
+}
+
+// ---- uniform path: the same exchange by the COPY ENGINES ------------------------------------------
+// A stage kernel holds every SM of the GPU (one CTA per SM, all registers), so a push KERNEL launched next to the
+// following stage only gets in when the first CTAs retire (70 us at 256^3), and then competes with them; at 8 GPUs
+// the boundary CTAs of the neighbours sat waiting for it (profiles/r02e_multigpu.md).  The copy engines need no SM:
+// a z layer is one 2-D peer copy (a whole padded plane per field, fields one pitch apart), a y layer one 2-D copy
+// per field (a padded row per plane), and the arrival counter follows in stream order as an 8-byte copy out of a
+// pinned ring of sequence numbers.  The padded rows / planes carry their own ghost cells along: those land in edge
+// and corner ghosts of the neighbour, which no interface touches.  x layers (8-byte elements a row apart) stay with
+// the push kernel: the default decompositions have no partition side across x.
+static int comm_uniform_dma_push(mmf_ctx *ctx, double *S, int a, bool defer_wait)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    unsigned int mask = 0;
+    for (int s = 2; s < 6; ++s) mask |= (u->nbr_rank[s] >= 0) ? (1u << s) : 0u;
+    if (!mask) return MMF_OK;
+    const unsigned long long seq = ++u->xchg_seq;
+    const bool async = defer_wait && u->push_async;
+    cudaStream_t ps = ctx->stream;
+    if (async) { // next to the following stage
+        MMF_CUDA(ctx, cudaEventRecord(u->ev_stage, ctx->stream));
+        MMF_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, u->ev_stage, 0));
+        ps = ctx->comm_stream;
+    }
+    const size_t row = (size_t) g.px * sizeof(double), plane = row * g.py, field = (size_t) g.fs * sizeof(double);
+    for (int s = 2; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        const int axis = s >> 1;
+        const bool hi = s & 1;
+        const int n_ax = (axis == 1) ? g.ny : g.nz;
+        const int own = hi ? n_ax - 1 : 0, ghost = hi ? -1 : n_ax; // my layer -> the neighbour's ghost layer
+        const char *src = reinterpret_cast<const char *>(S);
+        char *dst = reinterpret_cast<char *>(u->peer_arr[s][a]);
+        if (axis == 2) {
+            MMF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t) (ghost + 1) * plane, field, src + (size_t) (own + 1) * plane, field,
+                                            plane, NF, cudaMemcpyDefault, ps));
+        } else if (field == plane * g.pz) { // the fields follow each other without a gap: one copy for all of them
+            MMF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t) (ghost + 1) * row, plane, src + (size_t) (own + 1) * row, plane,
+                                            row, (size_t) g.pz * NF, cudaMemcpyDefault, ps));
+        } else {
+            for (int f = 0; f < NF; ++f) {
+                MMF_CUDA(ctx, cudaMemcpy2DAsync(dst + f * field + (size_t) (ghost + 1) * row, plane,
+                                                src + f * field + (size_t) (own + 1) * row, plane, row, g.pz, cudaMemcpyDefault, ps));
+            }
+        }
+    }
+    unsigned long long *slot = u->seq_ring + (seq % DMA_SEQ_RING);
+    *slot = seq; // (the host runs at most a few steps ahead of the device: mmf_run synchronises every 8 steps)
+    for (int s = 2; s < 6; ++s) {
+        if (u->nbr_rank[s] < 0) continue;
+        MMF_CUDA(ctx, cudaMemcpyAsync(u->peer_flags[s], slot, sizeof(unsigned long long), cudaMemcpyDefault, ps));
+    }
+    if (async) {
+        MMF_CUDA(ctx, cudaEventRecord(u->ev_push[a], ctx->comm_stream));
+        u->push_pending[a] = true;
+    }
+    u->arr_seq[a] = seq;
+    if (!defer_wait) { // nobody downstream waits in-kernel: block the stream until all neighbours have delivered
+        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
 }
 
 static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
@@ -419,6 +491,7 @@ static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
     int a = -1;
     for (int q = 0; q < 3; ++q) if (S == u->arr[q]) a = q;
     if (a < 0) return fail(ctx, MMF_ERR_STATE, "peer exchange is defined for the U / W arrays only");
+    if (u->dma_push) return comm_uniform_dma_push(ctx, S, a, defer_wait);
     PushArgs args{};
     unsigned int mask = 0;
     int n_slots = 0;

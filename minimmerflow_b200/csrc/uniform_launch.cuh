@@ -68,6 +68,10 @@ struct UniformPath {
     unsigned long long xchg_seq = 0;
     unsigned long long arr_seq[3] = { 0, 0, 0 }; // exchange that last refreshed the ghosts of U / Wa / Wb
     bool halo_inkernel = false;       // boundary CTAs of the stage kernels wait for the neighbours themselves
+    // exchange by the copy engines (comm.cuh: comm_uniform_dma_push): y and z layers travel as strided peer copies, the
+    // arrival counters as 8-byte copies out of a pinned ring of sequence numbers -- no SM involved
+    bool dma_push = false;
+    unsigned long long *seq_ring = nullptr;   // pinned host memory, DMA_SEQ_RING entries
     int *tile_order[4] = {};          // per stage shape: interior tiles first, tiles on a partition side last
     // the push of a stage's output runs on the communication stream, next to the interior tiles of the
     // following stage; allowed only when every stage has at least one full wave of interior tiles, so

@@ -62,7 +62,9 @@ static int uniform_build_tile_orders(mmf_ctx *ctx)
             for (int s = 0; s < 6; ++s) waits = waits || (side[s] && u->nbr_rank[s] >= 0);
             (waits ? outer : inner).push_back(t);
         }
-        if (st >= 1) u->push_async = u->push_async && (int) inner.size() >= ctx->prop.multiProcessorCount;
+        // (a push KERNEL needs an SM: waiting boundary CTAs must never hold all of them before it has been scheduled;
+        //  the copy engines do not care)
+        if (st >= 1 && !u->dma_push) u->push_async = u->push_async && (int) inner.size() >= ctx->prop.multiProcessorCount;
         inner.insert(inner.end(), outer.begin(), outer.end());
         int rc = dev_upload(ctx, &u->tile_order[st], inner);
         if (rc) return rc;

@@ -1,6 +1,8 @@
-"""Two-GPU parity (one process per GPU, NCCL over NVLink), through the C-ABI.
+"""Multi-GPU parity (one process per GPU, NCCL over NVLink), through the C-ABI.
 
-(1) uniform path: the 32^3 cube split into two z boxes (the Morton chunks of a 2-rank partition);
+(1) uniform path: the 32^3 cube split into 2 / 4 / 8 boxes: z halves, z-y quarters, octants (the Morton chunks of a
+    2 / 4 / 8-rank partition; the octants put BOTH x sides of every box on compact ghost columns) and the 1x2x4 slabs
+    bench.py runs at 8 GPUs (no partition side across x);
 (2) generic path: Morton-chunk partition with one ghost layer and explicit send / receive lists
     (the role of GhostCommunicator, src/communications.cpp:609-741).
 Both must reproduce the SERIAL oracle bit for bit on every rank's interior cells -- the reference
@@ -64,6 +66,8 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
             grid = (world, 1, 1)       # partition side on x: compact ghost columns (XGhost)
         elif mode.endswith("_y"):
             grid = (1, world, 1)
+        elif mode.endswith("_yz"):
+            grid = {2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}[world]   # no partition side across x
         dims = (n // grid[0], n // grid[1], n // grid[2])
         offset, nbrs = box_of_rank(rank, grid, dims)
         ijk = m["cell_ijk"]
@@ -107,10 +111,24 @@ def _worker(rank, world, mode, problem, n, steps, out_dir):
                                           ("uniform", "vortex_xy"), ("uniform", "radsod"), ("uniform_x", "radsod"),
                                           ("generic", "vortex_xy")])
 def test_two_gpu_run_equals_serial_oracle(mmf, oracle, tmp_path, mode, problem):
-    if mmf.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    _run_and_compare(mmf, oracle, tmp_path, mode, problem, 2)
+
+
+@pytest.mark.parametrize("world,mode,problem", [(4, "uniform_p2p", "vortex_xy"), (4, "uniform_p2p", "radsod"), (4, "uniform", "radsod"),
+                                                (8, "uniform_p2p", "vortex_xy"), (8, "uniform_p2p", "radsod"),
+                                                (8, "uniform_p2p_yz", "vortex_xy"), (8, "uniform_p2p_yz", "radsod"),
+                                                (8, "uniform", "vortex_xy"), (4, "generic", "vortex_xy")])
+def test_four_and_eight_gpu_runs_equal_serial_oracle(mmf, oracle, tmp_path, world, mode, problem):
+    """The reference wants the same golden string from 1 and 3 ranks (test/CMakeLists.txt:124-126); here every layout
+    bench.py runs -- z-y quarters, the 2x2x2 octants (x partition sides) and the 1x2x4 slabs -- against the serial oracle."""
+    _run_and_compare(mmf, oracle, tmp_path, mode, problem, world)
+
+
+def _run_and_compare(mmf, oracle, tmp_path, mode, problem, world):
+    if mmf.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (run under gpurun --gpus {world})")
     import torch.multiprocessing as mp
-    world, n, steps = 2, 32, 5
+    n, steps = 32, 5
     mp.spawn(_worker, args=(world, mode, problem, n, steps, str(tmp_path)), nprocs=world, join=True)
     m = oracle.problem_mesh(problem, 3, n)
     Uo = oracle.init_state(m)
