@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-level", type=int, default=0, help="oracle-port mesh level for the CPU legs (0 = 7)")
     ap.add_argument("--cpu-size", type=int, default=0, help="cells per side for the compiled-reference CPU leg (0 = 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strict", action="store_true", help="skip the timing of the strict drop-in call (mmf_compute_rhs_host)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check that precedes the timed region")
     ap.add_argument("--repeats", type=int, default=5,
                     help="the timed region (exactly --steps steps between barriers) is run this many times; the line reports "
@@ -127,6 +128,12 @@ def stage_kernel_label():
     else:
         label = label.replace("<2>", "<2|3>")
     return label + " (stages 2 and 3: two of the three launches of an RK3 step)"
+
+
+# FP64 instructions per cell and stage in the stage kernels' SASS (profiles/r02d_experiments.md: 224 of 526 instructions
+# per updated plane of a warp at stage 2; stage 1 has the shorter RK update) and the measured FP64 issue rate
+FP64_INSTR_PER_CELL_STAGE = (214, 224, 224)
+FP64_LANES_PER_CLK_SM = 61.2
 
 
 def measured_peak():
@@ -229,12 +236,18 @@ def run_reference(args):
         "steps": steps, "warmup": 0 if entry["kind"] == "reference" else 1,
         "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(dims, gdims, (px, py, pz)),
+        "config": dict(workload_config(dims, gdims, (px, py, pz)),
+                       sample_run=entry["sample"],
+                       sample_note="the workload / decomposition keys name the GPU arm's configuration (the driver pairs the two "
+                                   "lines by them); what THIS line timed is sample_run: a bounded CPU sample of the same problem"),
         "cpu_baseline": entry,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU arm: the reference's own implementation of the path on the host cores, on a bounded sample "
-                "of the workload (see cpu_baseline.sample)",
+        "note": "CPU arm: the reference's own implementation of the path (src/euler.cpp, src/main.cpp time loop, unmodified) on "
+                "the host cores, on a bounded sample of the workload (config.sample_run).  It is built against compat/bitpit, "
+                "this repository's stand-in for the bitpit containers and octree (bitpit itself is not available offline): "
+                "id -> position look-ups and iteration cost whatever the stand-in makes them cost, and the replicas do not "
+                "communicate -- a stated baseline, not a tuned competitor",
     }
     if port is not None:
         line["cpu_port_all_cores"] = port
@@ -254,7 +267,8 @@ def local_dims(args, grid):
 def workload_config(dims, gdims, grid):
     return {"workload": f"3-D isentropic vortex (vortex_xy), uniform {gdims[0]}x{gdims[1]}x{gdims[2]} cells "
                         f"({dims[0]}x{dims[1]}x{dims[2]} per GPU), order 1, CFL 0.45, free-flow borders, fixed step count",
-            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: direct peer stores over NVLink overlapped with interior tiles, scalar all-reduce: NCCL)",
+            "decomposition": f"{grid[0]}x{grid[1]}x{grid[2]} boxes (halo: peer copies over NVLink by the copy engines next to the following "
+                             f"stage, boundary tiles wait in-kernel and run last; scalar all-reduces: NCCL)",
             "path": "uniform fused stage kernels",
             "l2": "state arrays (2.0 GB at 256^3) >> 126 MB L2, no flush needed"}
 
@@ -461,6 +475,25 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # the STRICT drop-in call: euler::computeRHS with caller-owned host storages (mmf_compute_rhs_host: upload U,
+    # residual kernel, download RHS and the max eigenvalue on every call) -- what the adapter of INTEGRATION.md costs
+    # when main.cpp stays entirely unchanged; PCIe bound by construction.  One GPU only, pageable numpy buffers.
+    strict = None
+    if world == 1 and not args.no_strict:
+        Uh = np.ascontiguousarray(host.reshape(-1, 5))
+        Rh = np.empty_like(Uh)
+        s.compute_rhs_host(Uh, out=Rh)                                # warm-up (allocates the RHS array)
+        t0 = time.perf_counter()
+        n_calls = 3
+        for _ in range(n_calls):
+            s.compute_rhs_host(Uh, out=Rh)
+        strict_s = (time.perf_counter() - t0) / n_calls
+        strict = {"value": cells_local / strict_s, "unit": "cell residuals/s", "ms_per_call": strict_s * 1e3,
+                  "h2d_bytes_per_call": nbytes, "d2h_bytes_per_call": nbytes + 8,
+                  "what": "mmf_compute_rhs_host = euler::computeRHS with host storages: upload, residual kernel, download, "
+                          "wall clock; one call is one RK stage's residual (a third of a cell-update's work, none of its update)"}
+        del Uh, Rh
+
     if dist is not None:
         import torch
         tt = torch.tensor([e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -479,14 +512,22 @@ def run_ours(args):
         dom_ms = (kms[2] + kms[3]) / max(kn[2] + kn[3], 1)
         achieved = ALG_BYTES_PER_CELL_STAGE[1] * cells_local / (dom_ms * 1e-3) / 1e9 if dom_ms else None
         step_gbs = sum(ALG_BYTES_PER_CELL_STAGE) * cells_local / (ms / args.steps * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes of one launch of the dominant kernel: from the round's own `ncu --set full` capture of this
+        # configuration (tools/make_profiles.py writes the file and the commit it was taken at), never under the timer
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")) as f:
                 tj = json.load(f)
             if tj.get("cells_per_launch") == cells_local:
                 traffic = tj["stage23_dram_bytes_per_launch"]
+                traffic_src = {k: tj.get(k) for k in ("source", "commit", "kernel")}
         except Exception:
             pass
+        # secondary limiter: the FP64 pipe.  Algorithmic FP64 instructions per cell and stage (the
+        # reference's arithmetic without FMA contraction, primitives once per cell) over the measured issue rate of the
+        # pipe (profiles/r02_fp64_peak.md: tools/ubench_fp64 on this pool's B200)
+        fp64_peak = FP64_LANES_PER_CLK_SM * 148 * 1.965e9
+        fp64_ach = FP64_INSTR_PER_CELL_STAGE[1] * cells_local / (dom_ms * 1e-3) if dom_ms else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -501,10 +542,17 @@ def run_ours(args):
             "e2e": {"value": cells_total * 3.0 * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": nbytes / args.steps, "d2h_bytes_per_step": nbytes / args.steps + 88,
                     "what": f"pinned host AoS upload, {args.steps} x mmf_step (dt and max eigenvalues read back and the host "
-                            f"synchronised every step), download; wall clock through the C-ABI"},
+                            f"synchronised every step), download; wall clock through the C-ABI.  The state is resident between "
+                            f"the steps, so the upload and the download are amortised over --steps",
+                    "strict_dropin": strict},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
+                         "secondary": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "FP64 lane-instructions/s",
+                                       "frac": (fp64_ach / fp64_peak) if fp64_ach else None,
+                                       "what": f"{FP64_INSTR_PER_CELL_STAGE[1]} FP64 instructions per cell of stage 2/3 (algorithmic: "
+                                               f"halo and padding work not counted) over {FP64_LANES_PER_CLK_SM} lanes/clk/SM x 148 SMs "
+                                               f"x 1.965 GHz measured"},
                          "kernel": stage_kernel_label(),
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE[1] * cells_local,
                          "avg_launch_ms": dom_ms,

@@ -82,7 +82,10 @@ def main():
             return int(m.group(1)) if m else -1
         t23 = [gb(r, "dram__bytes_read.sum") + gb(r, "dram__bytes_write.sum") for r, n in zip(rows, names) if stage_of(n) in (2, 3)]
         t1 = [gb(r, "dram__bytes_read.sum") + gb(r, "dram__bytes_write.sum") for r, n in zip(rows, names) if stage_of(n) == 1]
+        commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        k23 = [re.sub(r"\(mmf::UniformGeom.*", "", n).replace("void mmf::", "") for n in names if stage_of(n) in (2, 3)]
         json.dump({"source": f"profiles/{args.tag}_ncu_stage_kernels.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
+                   "commit": commit, "kernel": sorted(set(k23)),
                    "cells_per_launch": args.cells,
                    "stage23_dram_bytes_per_launch": sum(t23) / max(len(t23), 1),
                    "stage1_dram_bytes_per_launch": sum(t1) / max(len(t1), 1),
@@ -98,20 +101,20 @@ def main():
         text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
         chunks = re.split(r"\n(?=\s*Function : )", text)
         # (ELb0 = padded x ghost columns: the single-GPU instantiation the bench runs)
-        want = {"uniform_stage_kernel_v5ILi0ELi0ELi16ELb0": "stage0_rhs_only_v5_16warps",
-                "uniform_stage_kernel_v5ILi1ELi0ELi16ELb0": "stage1_v5_16warps",
+        want = {"uniform_stage_kernel_tILi0ELi0ELi16ELi4E": "stage0_rhs_only_t_16warps",
+                "uniform_stage_kernel_tILi1ELi0ELi16ELi4E": "stage1_t_16warps",
+                "uniform_stage_kernel_tILi2ELi0ELi16ELi4E": "stage2_t_16warps",
+                "uniform_stage_kernel_tILi3ELi0ELi16ELi4E": "stage3_t_16warps",
+                # the rotate form (per-thread global loads): what runs when an x side is a partition side
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb0": "stage2_v5r_12warps",
-                "uniform_stage_kernel_v5rILi3ELi0ELi12ELb0": "stage3_v5r_12warps",
-                # candidates not yet timed on the GPU (opt-in forms d / h / w / b), stage 2
-                "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb0": "candidate_stage2_v6_12warps",
-                "uniform_stage_kernel_v6ILi2ELi0ELi12ELb0ELb1": "candidate_stage2_v6h_12warps",
-                "uniform_stage_kernel_v7ILi2ELi0ELi8ELb0": "candidate_stage2_v7_8warps",
-                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb0": "candidate_stage2_v5rb_bodies_12warps",
-                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb1": "candidate_stage2_v5rb_bodies_fixup_12warps",
-                "uniform_wall_cells_kernelILi2ELi0": "candidate_stage2_wall_cells",
-                "uniform_eig_body_kernel": "candidate_uniform_eig_body",
+                "uniform_stage_kernel_v5rILi2ELi0ELi12ELb1": "stage2_v5r_12warps_xghost",
+                # a box with bodies: the rotate form that skips flagged cells, and the pass over the wall cells
+                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb1": "stage2_v5rb_bodies_12warps",
+                "uniform_wall_cells_kernelILi2ELi0": "stage2_wall_cells",
+                "uniform_eig_body_kernel": "uniform_eig_body",
                 "uniform_eig_kernel": "uniform_eig", "uniform_ghost_kernel": "uniform_ghost",
-                "generic_rhs_kernel": "generic_rhs", "generic_rk_kernelILi1": "generic_rk_stage1",
+                "generic_rhs_kernel": "generic_rhs", "generic_rhs_derived_kernel": "generic_rhs_derived",
+                "generic_stage_kernelILi2": "generic_stage2_fused", "generic_rk_kernelILi1": "generic_rk_stage1",
                 "uniform_layer_kernel": "uniform_layer_pack"}
         for c in chunks:
             m = re.match(r"\s*Function : (\S+)", c)
