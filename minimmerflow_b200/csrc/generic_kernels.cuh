@@ -366,6 +366,26 @@ __global__ void begin_step_kernel(StepControl *ctl, int have_candidate)
     ctl->eig_next    = 0.0;
 }
 
+// begin_step_kernel with a candidate followed by choose_dt_kernel, as one launch: the steady state of the uniform path
+__global__ void begin_step_choose_dt_kernel(StepControl *ctl)
+{
+    const double eig = ctl->eig_next;
+    ctl->max_eig[0]  = eig;
+    ctl->max_eig[1]  = 0.0;
+    ctl->max_eig[2]  = 0.0;
+    ctl->max_eig_chk = 0.0;
+    ctl->eig_next    = 0.0;
+    if (ctl->t < ctl->t_max) {
+        double dt = 0.9 * ctl->cfl * ctl->min_h / eig;
+        if (ctl->t + dt > ctl->t_max) dt = ctl->t_max - ctl->t;
+        ctl->dt     = dt;
+        ctl->active = 1.0;
+    } else {
+        ctl->dt     = 0.0;
+        ctl->active = 0.0;
+    }
+}
+
 // host-chosen dt (mmf_rk_stage keeps main.cpp's own dt logic on the host)
 __global__ void set_dt_kernel(StepControl *ctl, double dt)
 {

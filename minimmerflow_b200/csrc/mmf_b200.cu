@@ -208,6 +208,7 @@ extern "C" int mmf_destroy(mmf_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     trace_report(ctx);
+    for (cudaGraphExec_t &ge : ctx->gen_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
     comm_destroy(ctx);
     uniform_destroy(ctx);
     for (void *p : ctx->owned) cudaFree(p);
@@ -444,11 +445,45 @@ extern "C" int mmf_rk_stage(mmf_ctx *ctx, int stage, double dt)
     return MMF_OK;
 }
 
+static int generic_step_enqueue(mmf_ctx *ctx);
+
 // one RK3 step on the stream; the control block already holds t, t_max, cfl, min_h
 static int step_enqueue(mmf_ctx *ctx)
 {
-    int rc;
     if (ctx->path == MMF_PATH_UNIFORM) return uniform_step(ctx);
+    // One GPU, nothing timed per launch: the launches of a step are the same every time, up to the two work arrays
+    // of the fused stages swapping roles from one step to the next -- one captured CUDA graph per role assignment,
+    // replayed with one host call per step (the reference's own 64^2 / 32^3 sized cases are launch bound).
+    static const bool graphs_on = !(getenv("MMF_STEP_GRAPH") && atoi(getenv("MMF_STEP_GRAPH")) == 0);
+    if (!graphs_on || ctx->comm || ctx->profiling || ctx->tracing) return generic_step_enqueue(ctx);
+    const int role = (ctx->w_alt && ctx->fields[MMF_FIELD_W] > ctx->w_alt) ? 1 : 0;
+    double *w0 = ctx->fields[MMF_FIELD_W], *a0 = ctx->w_alt;
+    if (!ctx->gen_graph[role]) {
+        const int64_t launches0 = ctx->kernel_launches;
+        MMF_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = generic_step_enqueue(ctx);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        // (captured, not run: the role swap the enqueue did is undone and redone by the launch below)
+        ctx->fields[MMF_FIELD_W] = w0; ctx->w_alt = a0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) return fail(ctx, MMF_ERR_CUDA, "capture of a step failed: %s", cudaGetErrorString(e));
+        const cudaError_t ei = cudaGraphInstantiate(&ctx->gen_graph[role], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(ctx, MMF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        ctx->gen_graph_launches = (int) (ctx->kernel_launches - launches0);
+        ctx->kernel_launches = launches0;
+    }
+    MMF_CUDA(ctx, cudaGraphLaunch(ctx->gen_graph[role], ctx->stream));
+    ctx->kernel_launches += ctx->gen_graph_launches;
+    if (ctx->generic_fused) std::swap(ctx->fields[MMF_FIELD_W], ctx->w_alt); // what stage 2 of the replayed step did
+    ctx->state_valid[MMF_FIELD_W] = true;
+    return MMF_OK;
+}
+
+static int generic_step_enqueue(mmf_ctx *ctx)
+{
+    int rc;
     // unfused reference-shaped sequence (src/main.cpp:383-506)
     if ((rc = rhs_enqueue(ctx, MMF_FIELD_U, 0, ctx->generic_fused))) return rc;
     if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &ctx->d_ctl->max_eig[0], 1))) return rc;

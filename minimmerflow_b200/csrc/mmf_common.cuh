@@ -43,6 +43,8 @@ struct mmf_ctx {
     // (generic_stage_kernel); stage 2 then writes the second work array and the two swap roles
     bool generic_fused = false;
     double *w_alt = nullptr;
+    cudaGraphExec_t gen_graph[2] = { nullptr, nullptr }; // the launches of a step, captured per role of the two work arrays
+    int gen_graph_launches = 0;
     std::vector<void *> owned;                         // every cudaMalloc'd pointer of the handle
 
     // shared

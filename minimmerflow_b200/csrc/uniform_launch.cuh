@@ -43,6 +43,8 @@ struct UniformPath {
     struct InMap { const double *arr; int rows; TmaDesc map; };
     std::vector<InMap> in_maps;
     bool eig_candidate = false;       // ctl->eig_next holds the max eigenvalue of the current U
+    cudaGraphExec_t step_graph = nullptr; // the launches of a steady-state step, captured once (uniform_path.cuh: uniform_step)
+    int step_graph_launches = 0;
     bool clamp_ff = true;             // free-flow ghosts are never read by the stage kernels (LoadClamp)
     // bodies: one flag per padded cell, 1 = not solved (src/main.cpp:221-237), 2 = fluid cell with a wall interface,
     // which the stage kernel does not store and wall_cell_update recomputes (list of their padded offsets, compact

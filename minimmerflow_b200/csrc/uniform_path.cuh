@@ -20,6 +20,7 @@ inline void uniform_invalidate_eig(mmf_ctx *ctx) { if (ctx->uni) ctx->uni->eig_c
 inline void uniform_destroy(mmf_ctx *ctx)
 {
     if (ctx->uni) {
+        if (ctx->uni->step_graph) cudaGraphExecDestroy(ctx->uni->step_graph);
         if (ctx->uni->ev_stage) cudaEventDestroy(ctx->uni->ev_stage);
         for (cudaEvent_t e : ctx->uni->ev_push) if (e) cudaEventDestroy(e);
     }
@@ -146,7 +147,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     }
     // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
     // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
-    // derives for its first z interface; chunks stay between 16 and 96 planes.
+    // derives for its first z interface; chunks stay between 4 and 96 planes (a small box -- the reference's own 32^3
+    // cases -- fills the SMs only with short chunks: a CTA marches through its planes one after the other, 1.8 us each).
     u->clamp_ff = true;
     u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));
     const char *env_lz = getenv("MMF_STAGE_LZ");
@@ -156,7 +158,7 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.rows() - 1) / sh.rows());
         const double sms = (double) ctx->prop.multiProcessorCount;
         double best = -1.;
-        for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 16); ++chunks) {
+        for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 4); ++chunks) {
             const int lz = (g.nz + chunks - 1) / chunks;
             const long long n_chunks = (g.nz + lz - 1) / lz;
             const double waves = (double) (tiles_xy * n_chunks) / sms;
@@ -361,7 +363,7 @@ int comm_allreduce_max_enqueue(mmf_ctx *ctx, double *d_value, int count); // com
 //   max eigenvalue of U -> dt on the device -> three fused residual+update kernels, each followed by
 //   the ghost refresh of its output; behind stage 3 the max eigenvalue of the new U is found from the
 //   stage's per-tile estimates, so the next step starts without a pass over U.
-static int uniform_step(mmf_ctx *ctx)
+static int uniform_step_enqueue(mmf_ctx *ctx)
 {
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
@@ -370,21 +372,27 @@ static int uniform_step(mmf_ctx *ctx)
     double *U = u->arr[0], *Wa = u->arr[1], *Wb = u->arr[2];
 
     trace_point(ctx, "gap");
-    begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, u->eig_candidate ? 1 : 0);
-    MMF_LAUNCH_CHECK(ctx);
-    if (u->bodies) { // a box with bodies: a full pass every step (wall images have their own eigenvalue)
-        dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
-        uniform_eig_body_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, u->solid, &c->max_eig[0]);
+    if (u->eig_candidate && !u->bodies) {
+        // steady state: eig_next was found (and reduced over the ranks) at the end of the previous step
+        begin_step_choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
         MMF_LAUNCH_CHECK(ctx);
-    } else if (!u->eig_candidate) { // first step after the host (re)wrote U: full pass (+ all-reduce)
-        dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
-        uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
+    } else {
+        begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, 0);
         MMF_LAUNCH_CHECK(ctx);
-        if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
-    } // else: eig_next was reduced over the ranks at the end of the previous step
+        if (u->bodies) { // a box with bodies: a full pass every step (wall images have their own eigenvalue)
+            dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
+            uniform_eig_body_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, u->solid, &c->max_eig[0]);
+            MMF_LAUNCH_CHECK(ctx);
+        } else { // first step after the host (re)wrote U: full pass (+ all-reduce)
+            dim3 grid((g.nx + 2 + 255) / 256, g.ny + 2, (g.nz + 2 + EIG_ZCHUNK - 1) / EIG_ZCHUNK);
+            uniform_eig_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, &c->max_eig[0]);
+            MMF_LAUNCH_CHECK(ctx);
+            if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->max_eig[0], 1))) return rc;
+        }
+        choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
+        MMF_LAUNCH_CHECK(ctx);
+    }
     u->eig_candidate = false;
-    choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
-    MMF_LAUNCH_CHECK(ctx);
     trace_point(ctx, "begin+dt");
 
     // the stage-1 kernel re-derives the same face maximum as a by-product; advance_time_kernel
@@ -405,11 +413,19 @@ static int uniform_step(mmf_ctx *ctx)
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
         const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.rows() - 1) / s3.rows();
-        uniform_eig_estmax_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max);
-        MMF_LAUNCH_CHECK(ctx);
-        if (ctx->comm && (rc = comm_allreduce_max_enqueue(ctx, &c->est_max, 1))) return rc;
-        uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max, u->eig_cand);
-        MMF_LAUNCH_CHECK(ctx);
+        if (ctx->comm) {
+            // the largest estimate is reduced over the ranks first: with its own maximum as the yardstick a rank that
+            // holds nothing but free stream -- a plateau of equal estimates -- would list every tile and pay a full pass
+            // over U (measured at 8 GPUs: 0.27 ms per step on those ranks against 0.03 ms for the all-reduce)
+            uniform_eig_estmax_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max);
+            MMF_LAUNCH_CHECK(ctx);
+            if ((rc = comm_allreduce_max_enqueue(ctx, &c->est_max, 1))) return rc;
+            uniform_eig_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max, u->eig_cand);
+            MMF_LAUNCH_CHECK(ctx);
+        } else {
+            uniform_eig_estmax_select_kernel<<<1, 1024, 0, ctx->stream>>>(u->cta_est, u->n_tiles3, &c->est_max, u->eig_cand);
+            MMF_LAUNCH_CHECK(ctx);
+        }
         uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 320, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.rows(),
                                                                                              s3.lz, &c->eig_next);
         MMF_LAUNCH_CHECK(ctx);
@@ -425,6 +441,37 @@ static int uniform_step(mmf_ctx *ctx)
     advance_time_kernel<<<1, 1, 0, ctx->stream>>>(c, 1);
     MMF_LAUNCH_CHECK(ctx);
     trace_point(ctx, "advance");
+    return MMF_OK;
+}
+
+// A step of the steady state (one GPU, the eigenvalue candidate at hand, nothing being timed per launch) is the same
+// seven launches with the same arguments every time: they are captured ONCE into a CUDA graph and replayed -- one
+// host call per step instead of seven, which is what a step costs on the reference's own 32^3 / 64^2 sized cases.
+// MMF_STEP_GRAPH=0 turns it off.
+static int uniform_step(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    static const bool graphs_on = !(getenv("MMF_STEP_GRAPH") && atoi(getenv("MMF_STEP_GRAPH")) == 0);
+    const bool steady = graphs_on && u->eig_candidate && !u->bodies && !ctx->comm && !ctx->profiling && !ctx->tracing && u->w_cur == 2;
+    if (!steady) return uniform_step_enqueue(ctx);
+    if (!u->step_graph) {
+        const int64_t launches0 = ctx->kernel_launches;
+        MMF_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = uniform_step_enqueue(ctx);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) return fail(ctx, MMF_ERR_CUDA, "capture of a step failed: %s", cudaGetErrorString(e));
+        const cudaError_t ei = cudaGraphInstantiate(&u->step_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(ctx, MMF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        u->step_graph_launches = (int) (ctx->kernel_launches - launches0);
+        ctx->kernel_launches = launches0; // captured, not run
+    }
+    MMF_CUDA(ctx, cudaGraphLaunch(u->step_graph, ctx->stream));
+    ctx->kernel_launches += u->step_graph_launches;
+    u->eig_candidate = true;
+    u->w_cur = 2;
     return MMF_OK;
 }
 
