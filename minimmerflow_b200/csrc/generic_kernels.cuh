@@ -8,8 +8,14 @@
 #pragma once
 
 #include "generic_types.cuh"
+#include "ptx_helpers.cuh"
 
 namespace mmf {
+
+// resident blocks of 128 threads per SM the fused generic kernels are compiled for (5: up to 102 registers; measured: 4 = 0.463, 5 = 0.434, 6 = 0.399 ms per step on the 2-D 1024^2 vortex, but 6 loses 6 % on a two-level octree)
+#ifndef MMF_GEN_MINBLOCKS
+#define MMF_GEN_MINBLOCKS 5
+#endif
 
 // ---- host AoS (raw order, [c*5+k]) <-> device SoA ([k*stride+c]) -------------------------------
 
@@ -88,13 +94,41 @@ struct DerivedCell {
     double eto;  // p / (GAMMA-1) + 0.5 * rho * vel2   (src/euler.cpp:103)
 };
 
-__device__ __forceinline__ void derive_cell_generic(DerivedCell &d)
+// reciprocals of the two constants conservative2primitive / evalFluxes divide by, once per thread
+struct GenericDivConsts {
+    double y_gm1, y_c1; // 1 / (GAMMA-1), 1 / (2/(GAMMA-1))
+};
+
+__device__ __forceinline__ GenericDivConsts generic_div_consts()
 {
-    conservative2primitive(d.cons, d.prim);
+    GenericDivConsts k;
+    k.y_gm1 = rcp_nr(GM1);
+    k.y_c1  = rcp_nr(TWO_OVER_GM1);
+    return k;
+}
+
+// conservative2primitive + sound speed + |v|^2 + total energy of one cell.  The seven IEEE divisions share their
+// reciprocals (ptx_helpers.cuh: a / b == div_nr(a, b, rcp_nr(b)) bit for bit, mmf_selftest_division): four quotients
+// by rho cost one reciprocal, the two constants' reciprocals come from the caller -- the same construction as
+// derive_cell of the uniform path, a third of the FP64 instructions of seven stand-alone divisions.
+__device__ __forceinline__ void derive_cell_generic(DerivedCell &d, const GenericDivConsts &k)
+{
+    const double rho = d.cons[FID_RHO];
+    const double y   = rcp_nr(rho);
+    const double rr  = rho * rho;
+    const double yrr = rcp_nr(rr);
+    // src/utils.cpp:48-63
+    const double K = div_nr(d.cons[FID_RHO_U] * d.cons[FID_RHO_U] + d.cons[FID_RHO_V] * d.cons[FID_RHO_V] +
+                            d.cons[FID_RHO_W] * d.cons[FID_RHO_W], rr, yrr);
+    d.prim[FID_T] = div_nr(div_nr(2.0 * d.cons[FID_RHO_E], rho, y) - K, TWO_OVER_GM1, k.y_c1);
+    d.prim[FID_U] = div_nr(d.cons[FID_RHO_U], rho, y);
+    d.prim[FID_V] = div_nr(d.cons[FID_RHO_V], rho, y);
+    d.prim[FID_W] = div_nr(d.cons[FID_RHO_W], rho, y);
+    d.prim[FID_P] = rho * d.prim[FID_T];
     d.a = sqrt(GAMMA * d.prim[FID_T]);
     const double u = d.prim[FID_U], v = d.prim[FID_V], w = d.prim[FID_W];
     d.vel2 = u * u + v * v + w * w;
-    d.eto  = d.prim[FID_P] / GM1 + 0.5 * d.cons[FID_RHO] * d.vel2;
+    d.eto  = div_nr(d.prim[FID_P], GM1, k.y_gm1) + 0.5 * rho * d.vel2;
 }
 
 // euler::evalFluxes (src/euler.cpp:83-113) from a derived cell; un is the normal velocity evalSplitting
@@ -144,9 +178,10 @@ __device__ __forceinline__ void generic_cell_residual(const GenericMesh &m, cons
 {
     const int64_t e0 = m.cf_ptr[c], e1 = m.cf_ptr[c + 1];
     if (e0 == e1) return;
+    const GenericDivConsts dk = generic_div_consts();
     DerivedCell own;
     load_cell(S, m.stride, c, own.cons);
-    derive_cell_generic(own);
+    derive_cell_generic(own, dk);
     for (int64_t e = e0; e < e1; ++e) {
         const int32_t ent  = m.cf_ent[e];
         const int32_t f    = ent >> 1;
@@ -165,7 +200,7 @@ __device__ __forceinline__ void generic_cell_residual(const GenericMesh &m, cons
             const double flipped[3] = { -1. * nrm[0], -1. * nrm[1], -1. * nrm[2] };
             bc_values_of_derived(bc, flipped, m.dirichlet_info, own, other.cons);
         }
-        derive_cell_generic(other);
+        derive_cell_generic(other, dk);
 
         // euler::evalSplitting (src/euler.cpp:42-73) with L = owner, R = neighbour and the un-flipped normal (:232)
         double fOwn[NF], fOth[NF], unOwn, unOth;
@@ -294,7 +329,7 @@ __global__ void __launch_bounds__(256) generic_rk_kernel(int64_t n_cells, int64_
 //            out with the solution, src/main.cpp:284-298)
 // A step switched off on the device (ctl->active == 0) updates nothing, like generic_rk_kernel.
 template <int STAGE>
-__global__ void __launch_bounds__(128) generic_stage_kernel(GenericMesh m, const double *__restrict__ Sin,
+__global__ void __launch_bounds__(128, MMF_GEN_MINBLOCKS) generic_stage_kernel(GenericMesh m, const double *__restrict__ Sin,
                                                             const double *Un, double *Out, double *__restrict__ RHS,
                                                             const StepControl *__restrict__ ctl,
                                                             double *__restrict__ max_eig)
@@ -326,7 +361,7 @@ __global__ void __launch_bounds__(128) generic_stage_kernel(GenericMesh m, const
 
 // The stage-1 residual of the fused sequence: generic_rhs_kernel's result from generic_cell_residual (the
 // gathering cell derived once).  Stage 1 itself stays two kernels, its dt comes out of this one's maximum.
-__global__ void __launch_bounds__(128) generic_rhs_derived_kernel(GenericMesh m, const double *__restrict__ S,
+__global__ void __launch_bounds__(128, MMF_GEN_MINBLOCKS) generic_rhs_derived_kernel(GenericMesh m, const double *__restrict__ S,
                                                                   double *__restrict__ RHS, double *__restrict__ max_eig)
 {
     const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
