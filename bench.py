@@ -114,8 +114,9 @@ class ClockSampler(threading.Thread):
 
 def stage_kernel_label():
     """Name of the kernel that runs stages 2 and 3 (the dominant one), from the same knob the library reads."""
-    names = {"r": "uniform_stage_kernel_v5r", "t": "uniform_stage_kernel_t (input staged by bulk tensor loads)"}
-    shapes = ["t16"] * 4                                       # library defaults (uniform_path.cuh)
+    names = {"r": "uniform_stage_kernel_v5r", "t": "uniform_stage_kernel_t (input staged by bulk tensor loads)",
+             "h": "uniform_stage_kernel_t (input staged by bulk tensor loads, one warp for both halo rows)"}
+    shapes = ["h12"] * 4                                       # library defaults (uniform_path.cuh)
     cfg = [c for c in os.environ.get("MMF_STAGE_CFG", "").split(":") if c]
     if len(cfg) == 1:
         shapes = cfg * 4

@@ -3,7 +3,8 @@
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 //   r = the rotate form (uniform_stage_v5r.cuh), the default of every stage
 //   c = the rotate form for a box with bodies (uniform_stage_v5rb.cuh), wall cells by a small pass around it
-//   t = the same scheme with its input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh)
+//   t = the same scheme with its input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh);
+//       also serves form 'h' (one warp for both halo rows)
 #include "uniform_launch.cuh"
 
 #ifndef MMF_TU_FORM_ID // a bare `nvcc -c stage_tu.cu` (no Makefile): the rotate form, RHS only
@@ -52,10 +53,11 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
         if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16, true>, STAGE, 16, stage_v5_smem_bytes(16), Sin, Un, Out, d_max);
         return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>, STAGE, 12, stage_v5_smem_bytes(12), Sin, Un, Out, d_max);
     }
-#define MMF_LAUNCH_T(NWV, DV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV>, STAGE, NWV, stage_t_smem_bytes(NWV, STAGE, DV), Sin, Un, Out, d_max)
-    if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH);
-    if (sh.nw == 8) MMF_LAUNCH_T(8, T_DEPTH);
-    MMF_LAUNCH_T(12, T_DEPTH);
+#define MMF_LAUNCH_T(NWV, DV, MHV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV, MHV>, STAGE, NWV, MHV, stage_t_smem_bytes(NWV, STAGE, DV, MHV), Sin, Un, Out, d_max)
+    if (sh.form == 'h') { if (sh.nw == 12) MMF_LAUNCH_T(12, T_DEPTH, true); MMF_LAUNCH_T(16, T_DEPTH, true); }
+    if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH, false);
+    if (sh.nw == 8) MMF_LAUNCH_T(8, T_DEPTH, false);
+    MMF_LAUNCH_T(12, T_DEPTH, false);
 #undef MMF_LAUNCH_T
 #else
     const bool xgk = uniform_use_xghost(ctx);

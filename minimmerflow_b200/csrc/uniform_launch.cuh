@@ -16,13 +16,14 @@ namespace mmf {
 // which stage-kernel form runs a stage and with how many warps per CTA:
 //   'r' the rotate form of the low-face streaming kernel (uniform_stage_v5r.cuh), the default: 12 warps
 //   't' the same scheme with the input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh)
+//   'h' form 't' with ONE warp serving both halo rows of the tile: nw - 1 update rows per CTA
 //   'c' the rotate form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never
 //       by MMF_STAGE_CFG), the wall cells recomputed by a small pass around the stage kernel
 struct StageShape {
     char form = 'r';
     int nw = 12;
     int lz = 0; // planes per CTA
-    int rows() const { return nw - 2; } // y rows a CTA updates: all warps but the two halo rows
+    int rows() const { return form == 'h' ? nw - 1 : nw - 2; } // y rows a CTA updates: all warps but the halo warp(s)
     StageShape() = default;
     StageShape(char f, int n) : form(f), nw(n) {}
 };
@@ -238,19 +239,20 @@ static int uniform_in_map(mmf_ctx *ctx, const double *arr, int rows, const TmaDe
 }
 
 template <typename K>
-static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, size_t smem, const double *Sin, const double *Un, double *Out,
-                           double *d_max)
+static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, bool merged_halo, size_t smem, const double *Sin, const double *Un,
+                           double *Out, double *d_max)
 {
     UniformPath *u = ctx->uni;
+    const int nu = merged_halo ? nw - 1 : nw - 2; // update rows, tile rows = nu + 2
     const TmaDesc *smap = nullptr, *umap = nullptr;
-    if (int rc = uniform_in_map(ctx, Sin, nw, &smap)) return rc;
+    if (int rc = uniform_in_map(ctx, Sin, nu + 2, &smap)) return rc;
     const TmaDesc sm = *smap; // (the cache may grow below)
-    if (stage >= 2) { if (int rc = uniform_in_map(ctx, Un, nw - 2, &umap)) return rc; }
+    if (stage >= 2) { if (int rc = uniform_in_map(ctx, Un, nu, &umap)) return rc; }
     const TmaDesc um = umap ? *umap : sm;
     StageLaunchArgs a;
     MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
     if (int rc = stage_launch_prelude(ctx, stage, Sin, Out, a)) return rc;
-    if (a.xg.lo || a.xg.hi) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 't' does not read compact x ghost columns");
+    if (a.xg.lo || a.xg.hi) return fail(ctx, MMF_ERR_INVALID, "stage-kernel forms 't' / 'h' do not read compact x ghost columns");
     {
         ScopedLaunchTimer timer(ctx, stage);
         kern<<<a.grid, nw * 32, smem, ctx->stream>>>(u->g, Out, ctx->d_ctl, d_max, u->shape[stage].lz,
@@ -298,7 +300,7 @@ MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_t.cuh: input staged by bulk tensor loads
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('r', 'c', 't') for a stage
+// the launcher of a kernel form ('r', 'c', 't' / 'h') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
     static const StageLauncher tab[3][4] = {
@@ -306,7 +308,7 @@ inline StageLauncher stage_launcher(char form, int stage)
         { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
     };
-    return tab[(form == 'c') ? 1 : (form == 't') ? 2 : 0][stage];
+    return tab[(form == 'c') ? 1 : (form == 't' || form == 'h') ? 2 : 0][stage];
 }
 
 } // namespace mmf

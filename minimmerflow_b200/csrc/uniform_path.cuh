@@ -124,10 +124,11 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         MMF_LAUNCH_CHECK(ctx);
     }
     // Launch shapes, measured at 256^3 on B200 (profiles/r02d_experiments.md): the form whose input is staged by bulk
-    // tensor loads, at 16 warps (128 registers), is the fastest kernel of every stage.  MMF_STAGE_CFG overrides per
-    // stage, e.g. "r12:t16:t12:t12" (stage 0:1:2:3; 'r' = the rotate form with per-thread global loads, which is
-    // also what runs when an x side is a partition side).
-    for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 't', 16 };
+    // tensor loads with ONE warp for both halo rows, at 12 warps (168 registers: previous plane carried, loop unrolled
+    // by the ring depth), is the fastest kernel of every stage.  MMF_STAGE_CFG overrides per stage, e.g.
+    // "r12:t16:h16:h12" (stage 0:1:2:3; 't' = two halo warps, 'r' = the rotate form with per-thread global loads,
+    // which is also what runs when an x side is a partition side).
+    for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'h', 12 };
     if (const char *cfg = getenv("MMF_STAGE_CFG")) {
         int st = 0;
         for (const char *p = cfg; *p && st < 4;) {
@@ -137,7 +138,8 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             while (*p && *p != ':') ++p;
             const bool last = (*p == 0);
             if (*p == ':') ++p;
-            if ((sh.form != 'r' && sh.form != 't') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if ((sh.form != 'r' && sh.form != 't' && sh.form != 'h') || (sh.nw != 8 && sh.nw != 12 && sh.nw != 16)) break;
+            if (sh.form == 'h' && sh.nw == 8) sh.nw = 12;
             u->shape[st++] = sh;
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }

@@ -27,15 +27,18 @@
 
 namespace mmf {
 
+// planes per trip of the update rows' loop.  0 = by CTA size (measured, profiles/r02d_experiments.md): 4 = the ring depth
+// at 12 warps -- the slot of every unrolled copy is then a compile-time constant and 168 registers leave the compiler
+// room to overlap the copies --, 2 at 16 warps (128 registers)
 #ifndef MMF_T_UNROLL
-#define MMF_T_UNROLL 2
+#define MMF_T_UNROLL 0
 #endif
 // slots of the ring: two planes are being read (the current and the previous one), the others are in flight
 #ifndef MMF_T_DEPTH
 #define MMF_T_DEPTH 4
 #endif
 constexpr int T_DEPTH = MMF_T_DEPTH;
-constexpr int T_UNROLL = MMF_T_UNROLL;
+__host__ __device__ constexpr int t_unroll(int nw) { return MMF_T_UNROLL > 0 ? MMF_T_UNROLL : (nw <= 12 ? 4 : 2); }
 // experiment switches (profiles/r02d_experiments.md): the left x neighbour's U from the slot instead of five shuffles;
 // the ordered sum with a warp-uniform branch and two selects per field instead of three; the previous plane's U
 // carried in registers instead of read back from its slot
@@ -45,50 +48,62 @@ constexpr int T_UNROLL = MMF_T_UNROLL;
 #ifndef MMF_T_SELBR
 #define MMF_T_SELBR 1
 #endif
+// (-1 = by CTA size: carried at 12 warps, where the registers are there, re-read at 16)
 #ifndef MMF_T_CARRY
-#define MMF_T_CARRY 0
+#define MMF_T_CARRY -1
 #endif
 // the previous plane's slot handed back right after its last read (the z interface) instead of at the end of the step
 #ifndef MMF_T_EARLY_RELEASE
 #define MMF_T_EARLY_RELEASE 1
 #endif
 
-// ring geometry (doubles): a slot = the residual-input box [NF][NW][32] and, for stages 2 and 3, the U^n box
-// [NF][NW-2][32]; both are multiples of 128 bytes, which the destination of a bulk tensor copy must be aligned to
-__host__ __device__ constexpr int t_sin_doubles(int nw) { return NF * nw * 32; }
-__host__ __device__ constexpr int t_un_doubles(int nw, int stage) { return stage >= 2 ? NF * (nw - 2) * 32 : 0; }
-__host__ __device__ constexpr int t_slot_doubles(int nw, int stage) { return t_sin_doubles(nw) + t_un_doubles(nw, stage); }
-// behind the ring: records [NW][6][32] (Fy, lam_y), low y fluxes [NW][NF][32], then the mbarriers
-__host__ __device__ constexpr size_t stage_t_smem_bytes(int nw, int stage, int depth)
+// Rows of a CTA's tile.  Two halo warps (MH = false): warps 0 and NW-1 serve the low and the high halo row, NW-2 warps
+// update.  Merged halo warp (MH = true): warp 0 serves BOTH halo rows -- it publishes the record of the row below the
+// tile and turns the record of the tile's top row into that row's -y_hi; together that is 175 FP64 instructions per
+// plane against the 224 of an update row -- and NW-1 warps update: 15 rows per 16-warp CTA instead of 14.
+__host__ __device__ constexpr int t_update_rows(int nw, bool mh) { return mh ? nw - 1 : nw - 2; }
+__host__ __device__ constexpr int t_tile_rows(int nw, bool mh) { return t_update_rows(nw, mh) + 2; }
+
+// ring geometry (doubles): a slot = the residual-input box [NF][tile rows][32] and, for stages 2 and 3, the U^n box
+// [NF][update rows][32]; both are multiples of 128 bytes, which the destination of a bulk tensor copy must be aligned to
+__host__ __device__ constexpr int t_sin_doubles(int nw, bool mh) { return NF * t_tile_rows(nw, mh) * 32; }
+__host__ __device__ constexpr int t_un_doubles(int nw, int stage, bool mh) { return stage >= 2 ? NF * t_update_rows(nw, mh) * 32 : 0; }
+__host__ __device__ constexpr int t_slot_doubles(int nw, int stage, bool mh) { return t_sin_doubles(nw, mh) + t_un_doubles(nw, stage, mh); }
+// behind the ring: records [tile rows][6][32] (Fy, lam_y), low y fluxes [tile rows][NF][32], then the mbarriers
+__host__ __device__ constexpr size_t stage_t_smem_bytes(int nw, int stage, int depth, bool mh)
 {
-    return (size_t) (depth * t_slot_doubles(nw, stage) + nw * (6 + NF) * 32) * sizeof(double) +
-           (size_t) (2 * depth + 2 * nw) * sizeof(unsigned long long);
+    return (size_t) (depth * t_slot_doubles(nw, stage, mh) + t_tile_rows(nw, mh) * (6 + NF) * 32) * sizeof(double) +
+           (size_t) (2 * depth + 2 * t_tile_rows(nw, mh)) * sizeof(unsigned long long);
 }
 
-template <int STAGE, int ORDER, int NW, int D>
+template <int STAGE, int ORDER, int NW, int D, bool MH>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__restrict__ ctl, double *__restrict__ max_eig,
                        const int lz, float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw,
                        const __grid_constant__ TmaDesc smap, const __grid_constant__ TmaDesc umap)
 {
     extern __shared__ double smem[]; // (no static shared memory: the dynamic window starts 1 KB aligned)
-    constexpr int SLOT = t_slot_doubles(NW, STAGE);
-    constexpr int FSTR = NW * 32;        // field stride inside the residual-input box
-    constexpr int UFSTR = (NW - 2) * 32; // ... inside the U^n box
+    constexpr int NU = t_update_rows(NW, MH), NR = t_tile_rows(NW, MH); // rows the CTA updates / rows of its tile
+    constexpr bool CARRY = (MMF_T_CARRY < 0) ? (NW <= 12) : (MMF_T_CARRY != 0);
+    constexpr int UNROLL = t_unroll(NW);
+    constexpr int SLOT = t_slot_doubles(NW, STAGE, MH);
+    constexpr int SIN = t_sin_doubles(NW, MH), UN = t_un_doubles(NW, STAGE, MH);
+    constexpr int FSTR = NR * 32;        // field stride inside the residual-input box
+    constexpr int UFSTR = NU * 32;       // ... inside the U^n box
     double *ring = smem;
-    double *sm_r = smem + D * SLOT;            // records: sm_r[row][q][lane], q = Fy0..Fy4, lam_y
-    double *sm_f = sm_r + NW * 6 * 32;         // sm_f[row][k][lane] = area * flux of (j-1 | j)
-    unsigned long long *full  = reinterpret_cast<unsigned long long *>(sm_f + NW * NF * 32); // slot filled
+    double *sm_r = smem + D * SLOT;            // records: sm_r[tile row][q][lane], q = Fy0..Fy4, lam_y
+    double *sm_f = sm_r + NR * 6 * 32;         // sm_f[tile row][k][lane] = area * flux of (j-1 | j)
+    unsigned long long *full  = reinterpret_cast<unsigned long long *>(sm_f + NR * NF * 32); // slot filled
     unsigned long long *empty = full + D;      // slot handed back by all NW warps
-    unsigned long long *barD  = empty + D;     // record of row r published
-    unsigned long long *barF  = barD + NW;     // low y flux of row r published
+    unsigned long long *barD  = empty + D;     // record of tile row r published
+    unsigned long long *barF  = barD + NR;     // low y flux of tile row r published
 
     if (STAGE >= 1 && ctl->active == 0.0) return;
 
     const int lane = threadIdx.x & 31;
     const int row  = threadIdx.x >> 5;
     const TileId tid = stage_tile(hw);
-    if (threadIdx.x < NW) {
+    if (threadIdx.x < NR) {
         mbar_init(&barD[threadIdx.x], 1);
         mbar_init(&barF[threadIdx.x], 1);
     }
@@ -101,9 +116,9 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
     __syncthreads();
 
     const int i0 = tid.bx * XW - 1;        // cell coordinates of the box's first column / row
-    const int j0 = tid.by * (NW - 2) - 1;
+    const int j0 = tid.by * NU - 1;
     const int i  = i0 + lane;
-    const int j  = j0 + row;
+    const int j  = j0 + row;               // warp w works on tile row w (the merged halo warp: on rows 0 and NR-1)
     const int z0 = tid.bz * lz;
     const int z1 = min(z0 + lz, g.nz);
     const int nsteps = z1 - z0;            // planes this CTA updates; ring steps 0 .. nsteps+1 = planes z0-1 .. z1
@@ -115,6 +130,10 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
     const int ry_dn = min(max(j - 1, lc.jlo), lc.jhi) - j0;
     const int own = ry * 32 + cx;
     const int dn  = ry_dn * 32 + cx;
+    // the high halo row of the tile (tile row NR-1), for the warp that serves it
+    const int j_hi   = j0 + NR - 1;
+    const int own_hi = (min(max(j_hi, lc.jlo), lc.jhi) - j0) * 32 + cx;
+    const int dn_hi  = (min(max(j_hi - 1, lc.jlo), lc.jhi) - j0) * 32 + cx;
 
     const double Ah = 0.5 * g.area;
     DivConsts dc;
@@ -125,18 +144,48 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
     double lmax = 0.0;
     float emax = 0.f;
 
+    // ---- the high halo row's step: the y face (j-1 | j) between the tile's top row and the row above it -----------
+    double lmy_hi = 0.0;
+    auto high_halo_step = [&](const int s) {
+        const double *ts = ring + (s % D) * SLOT;
+        const double *r_dn = sm_r + (NR - 2) * 6 * 32 + lane;
+        double *f = sm_f + (NR - 1) * NF * 32 + lane;
+        double cU[NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own_hi];
+        CellPrim q;
+        derive_cell(cU, dc, q);
+        double cFy[NF], cly;
+        axis_flux<1>(q, cFy, cly);
+        double lU[NF], lF[NF], AFy[NF];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) lU[k] = ts[k * FSTR + dn_hi];
+        mbar_wait(&barD[NR - 2], (unsigned) ((s - 1) & 1));
+#pragma unroll
+        for (int k = 0; k < NF; ++k) lF[k] = r_dn[k * 32];
+        const double ll  = r_dn[NF * 32];
+        const double lam = llf_area_flux(lU, lF, ll, cU, cFy, cly, Ah, AFy);
+        lmy_hi = (lam < lmy_hi) ? lmy_hi : lam;
+        // the row below published this record only after it had read the previous flux: the slot is free
+#pragma unroll
+        for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
+        mbar_arrive_elect(&barF[NR - 1], lane);
+    };
+    const bool yf_ok_hi = in_x && lane >= 1 && lane <= XW && j_hi >= 0 && j_hi <= g.ny;
+
     if (row == 0) {
         // ================= low halo row: publishes (Fy, lam_y) of row j0 for row 1; lane 0 feeds the ring ==========
+        // (MH: the same warp then serves the high halo row)
         // step p: residual-input plane clamp(z0-1+p) and, for 1 <= p <= nsteps, U^n of plane z0-1+p
         auto produce = [&](const int p) {
             const int slot = p % D;
             if (p >= D) mbar_wait(&empty[slot], (unsigned) ((p / D - 1) & 1));
             const bool with_un = STAGE >= 2 && p >= 1 && p <= nsteps;
             double *dst = ring + slot * SLOT;
-            mbar_expect_tx(&full[slot], (unsigned) ((t_sin_doubles(NW) + (with_un ? t_un_doubles(NW, STAGE) : 0)) * sizeof(double)));
+            mbar_expect_tx(&full[slot], (unsigned) ((SIN + (with_un ? UN : 0)) * sizeof(double)));
             const int kp = min(max(z0 - 1 + p, lc.klo), lc.khi);
             tma_load_4d(&smap, dst, &full[slot], i0 + XOFF, j0 + 1, kp + 1, 0);
-            if (with_un) tma_load_4d(&umap, dst + t_sin_doubles(NW), &full[slot], i0 + XOFF, j0 + 2, z0 + p, 0);
+            if (with_un) tma_load_4d(&umap, dst + SIN, &full[slot], i0 + XOFF, j0 + 2, z0 + p, 0);
             mbar_arrive(&full[slot]);
         };
         // all D slots start out free: steps 0 .. D-1 go out at once; from then on the copy of step s+D-1 is issued at
@@ -164,40 +213,18 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             for (int k = 0; k < NF; ++k) r[k * 32] = cFy[k];
             r[NF * 32] = cly;
             mbar_arrive_elect(&barD[0], lane);
+            if (MH) high_halo_step(s);
             if (lane == 0 && s + D - 1 <= nsteps + 1) produce(s + D - 1);
         }
-    } else if (row == NW - 1) {
+        if (MH) lmax = yf_ok_hi ? lmy_hi : 0.0;
+    } else if (!MH && row == NW - 1) {
         // ================= high halo row: computes the y face (j-1 | j) for the row below ==========
-        const bool yf_ok = in_x && lane >= 1 && lane <= XW && j >= 0 && j <= g.ny;
-        const double *r_dn = sm_r + (NW - 2) * 6 * 32 + lane;
-        double *f = sm_f + (NW - 1) * NF * 32 + lane;
-        double lmy = 0.0;
         for (int s = 1; s <= nsteps; ++s) {
             mbar_arrive_elect(&empty[(s - 1) % D], lane);
             mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
-            const double *ts = ring + (s % D) * SLOT;
-            double cU[NF];
-#pragma unroll
-            for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own];
-            CellPrim q;
-            derive_cell(cU, dc, q);
-            double cFy[NF], cly;
-            axis_flux<1>(q, cFy, cly);
-            double lU[NF], lF[NF], AFy[NF];
-#pragma unroll
-            for (int k = 0; k < NF; ++k) lU[k] = ts[k * FSTR + dn];
-            mbar_wait(&barD[NW - 2], (unsigned) ((s - 1) & 1));
-#pragma unroll
-            for (int k = 0; k < NF; ++k) lF[k] = r_dn[k * 32];
-            const double ll  = r_dn[NF * 32];
-            const double lam = llf_area_flux(lU, lF, ll, cU, cFy, cly, Ah, AFy);
-            lmy = (lam < lmy) ? lmy : lam;
-            // the row below published this record only after it had read the previous flux: the slot is free
-#pragma unroll
-            for (int k = 0; k < NF; ++k) f[k * 32] = AFy[k];
-            mbar_arrive_elect(&barF[NW - 1], lane);
+            high_halo_step(s);
         }
-        lmax = yf_ok ? lmy : 0.0;
+        lmax = yf_ok_hi ? lmy_hi : 0.0;
     } else {
         // ================= update rows ==============================================================
         const bool upd   = lane >= 1 && lane <= XW && in_x && in_y;
@@ -220,7 +247,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
         double *op = Out + ((long long) (j + 1) * g.px + (i + XOFF)) + (long long) z0 * plane; // plane z0-1: the first store goes to z0
 
         double pFz[NF], plz, pS[NF];
-        double pUc[NF]; // (MMF_T_CARRY only)
+        double pUc[NF]; // (CARRY only)
         double lmx = 0.0, lmy = 0.0, lmz = 0.0;
         const int xl_idx = min(max(min(max(i - 1, lc.ilo), lc.ihi) - i0, 0), 31) + ry * 32; // the left x neighbour's cell in a slot
         // ---- step 0: plane z0-1 only provides the low side of the first z interface ------------------
@@ -239,7 +266,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             for (int k = 0; k < NF; ++k) pUc[k] = c0[k];
         }
 
-#pragma unroll T_UNROLL
+#pragma unroll UNROLL
         for (int s = 1; s <= nsteps; ++s) {
             const int kz = z0 + s - 1;
             const unsigned par = (unsigned) ((s - 1) & 1);
@@ -267,12 +294,12 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             {
                 double pU[NF], pUn[NF];
 #pragma unroll
-                for (int k = 0; k < NF; ++k) pU[k] = MMF_T_CARRY ? pUc[k] : tp[k * FSTR + own];
+                for (int k = 0; k < NF; ++k) pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own];
                 const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
                 lmz = (lam < lmz) ? lmz : lam;
                 if (STAGE >= 2) {
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) pUn[k] = tp[t_sin_doubles(NW) + k * UFSTR + un_own];
+                    for (int k = 0; k < NF; ++k) pUn[k] = tp[SIN + k * UFSTR + un_own];
                 }
                 finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && s > 1, est_max);
                 op += plane;
@@ -374,7 +401,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pS[k] = S[k]; pFz[k] = cFz[k]; }
             plz = clz;
-            if (MMF_T_CARRY) {
+            if (CARRY) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pUc[k] = cU[k];
             }
@@ -389,7 +416,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
             double cU[NF], pU[NF], pUn[NF];
 #pragma unroll
-            for (int k = 0; k < NF; ++k) { cU[k] = ts[k * FSTR + own]; pU[k] = MMF_T_CARRY ? pUc[k] : tp[k * FSTR + own]; }
+            for (int k = 0; k < NF; ++k) { cU[k] = ts[k * FSTR + own]; pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own]; }
             CellPrim q;
             derive_cell(cU, dc, q);
             double cFz[NF], clz, AFz[NF];
@@ -398,7 +425,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             lmz = (lam < lmz) ? lmz : lam;
             if (STAGE >= 2) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) pUn[k] = tp[t_sin_doubles(NW) + k * UFSTR + un_own];
+                for (int k = 0; k < NF; ++k) pUn[k] = tp[SIN + k * UFSTR + un_own];
             }
             finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
         }

@@ -25,7 +25,7 @@ def emu():
     return run_emu.load()
 
 
-@pytest.mark.parametrize("form", ["r", "t"])
+@pytest.mark.parametrize("form", ["r", "t", "h"])
 @pytest.mark.parametrize("chaos", [0, 300])
 def test_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, form, chaos):
     # Morton cube (the reference's numbering), z chunks of 6 planes: general and steady-state bodies
@@ -56,7 +56,7 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
     U0 = oracle.init_state(m)
     ref, ref_eig = oracle.compute_rhs(m, U0)
     out = {}
-    for form in ("r", "t"):
+    for form in ("r", "t", "h"):
         box = run_emu.Box(emu, oracle, dict(m), 2)
         U, R = box.new_array(), box.new_array()
         box.scatter(U, U0)
@@ -64,7 +64,7 @@ def test_axis_order_forms_agree_on_the_emulator(emu, oracle):
         eig, _ = box.stage(form, 0, 8, 5, U, U, R, 0.0, 200, 5)
         assert eig == ref_eig
         out[form] = box.gather(R)
-    assert np.array_equal(out["r"], out["t"])
+    assert np.array_equal(out["r"], out["t"]) and np.array_equal(out["r"], out["h"])
     assert np.abs(out["r"] - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
@@ -162,7 +162,7 @@ def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu,
 PLAIN_CASES_3D = [c for c in reference_cases() if c["dim"] == 3 and not c.get("bodies")]
 
 
-@pytest.mark.parametrize("form,nw", [("r", 12), ("t", 12), ("t", 16)])
+@pytest.mark.parametrize("form,nw", [("r", 12), ("t", 16), ("h", 12), ("h", 16)])
 @pytest.mark.parametrize("case", PLAIN_CASES_3D, ids=lambda c: c["name"])
 def test_stage_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case, form, nw):
     """Every stage-kernel form through

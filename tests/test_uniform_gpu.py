@@ -60,7 +60,7 @@ def test_random_state_rhs_bit_exact_all_bcs(mmf, oracle):
 
 
 @pytest.mark.parametrize("lz", ["5", "1", "2"])
-@pytest.mark.parametrize("cfg", ["", "r12", "r16", "r8", "t12", "t16", "t8", "r8:t12:t16:r12"])
+@pytest.mark.parametrize("cfg", ["", "r12", "r16", "r8", "t12", "t16", "t8", "h12", "h16", "r8:t12:h16:r12"])
 def test_fused_steps_bit_exact(mmf, oracle, monkeypatch, cfg, lz):
     """Every stage-kernel form and CTA shape (default first), ragged z chunks down to one- and two-plane chunks."""
     if cfg:

@@ -74,7 +74,7 @@ def load():
 
 def tile_rows(form, nw):
     """y rows a CTA of nw warps updates (StageShape::rows in uniform_launch.cuh)."""
-    return nw - 2
+    return nw - 1 if form == "h" else nw - 2
 
 
 def ia(v):
@@ -196,9 +196,10 @@ class Box:
 
     def smem_doubles(self, form, nw):
         base = nw * 16 * 32 + 2 * nw                 # records and fluxes, two mbarriers per row
-        if form == "t":                              # the ring of bulk tensor loads + records, fluxes, mbarriers (stage_t_smem_bytes)
+        if form in ("t", "h"):                       # the ring of bulk tensor loads + records, fluxes, mbarriers (stage_t_smem_bytes)
             depth = 4
-            return depth * 5 * 32 * (2 * nw - 2) + nw * 11 * 32 + 2 * depth + 2 * nw
+            nu = tile_rows(form, nw)
+            return depth * 5 * 32 * (2 * nu + 2) + (nu + 2) * 11 * 32 + 2 * depth + 2 * (nu + 2)
         return base
 
     def eig_body(self, arr):
@@ -310,7 +311,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="r,t,c")
+    ap.add_argument("--forms", default="r,t,h,c")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)

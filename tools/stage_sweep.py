@@ -88,7 +88,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--variants", default="r12,t12,t16,r16,r8")
+    ap.add_argument("--variants", default="h12,h16,t16,t12,r12")
     ap.add_argument("--variant-timeout", type=float, default=90.0,
                     help="seconds per variant: every variant runs in its own process, so a kernel form that hangs on real "
                          "hardware costs its own slot only")
