@@ -405,6 +405,15 @@ static int comm_ipc_import(mmf_ctx *ctx, const void *all_ranks)
     if (u->dma_push && !u->seq_ring) {
         MMF_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void **>(&u->seq_ring), DMA_SEQ_RING * sizeof(unsigned long long), cudaHostAllocDefault));
     }
+    // an x partition side keeps its ghosts in compact columns only the rotate form reads: the stages switch to it (same
+    // warps per CTA: 'h' at 12 warps updates 11 rows per tile, 'r' 10 -- tiles, z chunks and estimate buffers follow)
+    if (uniform_use_xghost(ctx)) {
+        bool changed = false;
+        for (int st = 0; st < 4; ++st) {
+            if (u->shape[st].form != 'r') { u->shape[st].form = 'r'; changed = true; }
+        }
+        if (changed) { if (int rc = uniform_setup_shapes(ctx)) return rc; }
+    }
     return uniform_build_tile_orders(ctx);
 }
 

@@ -48,11 +48,9 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     }
     return MMF_OK;
 #elif MMF_TU_FORM_ID == 2
-    // compact x ghost columns (an x partition side) are only read by the rotate form
-    if (uniform_use_xghost(ctx)) {
-        if (sh.nw == 16) return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 16, true>, STAGE, 16, stage_v5_smem_bytes(16), Sin, Un, Out, d_max);
-        return launch_stage_k(ctx, uniform_stage_kernel_v5r<STAGE, ORDER, 12, true>, STAGE, 12, stage_v5_smem_bytes(12), Sin, Un, Out, d_max);
-    }
+    // (compact x ghost columns -- an x partition side -- are only read by the rotate form: comm_ipc_import switches the
+    //  stages' shapes to it)
+    if (uniform_use_xghost(ctx)) return fail(ctx, MMF_ERR_STATE, "stage-kernel forms 't' / 'h' cannot read compact x ghost columns");
 #define MMF_LAUNCH_T(NWV, DV, MHV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV, MHV>, STAGE, NWV, MHV, stage_t_smem_bytes(NWV, STAGE, DV, MHV), Sin, Un, Out, d_max)
     if (sh.form == 'h') { if (sh.nw == 12) MMF_LAUNCH_T(12, T_DEPTH, true); MMF_LAUNCH_T(16, T_DEPTH, true); }
     if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH, false);

@@ -108,6 +108,44 @@ static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, dou
 
 // ---- creation -----------------------------------------------------------------------------------
 
+// Everything that follows from the stages' CTA shapes: the z chunk per CTA, the number of stage-3 tiles and the buffers
+// of the per-tile eigenvalue estimates.  Called at creation and again if the shapes change (comm_ipc_import: a box
+// with an x partition side runs the rotate form).
+static int uniform_setup_shapes(mmf_ctx *ctx)
+{
+    UniformPath *u = ctx->uni;
+    const UniformGeom &g = u->g;
+    int rc;
+    // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
+    // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
+    // derives for its first z interface; chunks stay between 4 and 96 planes (a small box -- the reference's own 32^3
+    // cases -- fills the SMs only with short chunks: a CTA marches through its planes one after the other, 1.8 us each).
+    const char *env_lz = getenv("MMF_STAGE_LZ");
+    for (int st = 0; st < 4; ++st) {
+        StageShape &sh = u->shape[st];
+        if (env_lz && atoi(env_lz) > 0) { sh.lz = atoi(env_lz); continue; }
+        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.rows() - 1) / sh.rows());
+        const double sms = (double) ctx->prop.multiProcessorCount;
+        double best = -1.;
+        for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 4); ++chunks) {
+            const int lz = (g.nz + chunks - 1) / chunks;
+            const long long n_chunks = (g.nz + lz - 1) / lz;
+            const double waves = (double) (tiles_xy * n_chunks) / sms;
+            const double score = waves / std::ceil(waves) * (double) lz / (lz + 1.0);
+            if (score > best + 1e-9) { best = score; sh.lz = lz; }
+        }
+        if (sh.lz <= 0) sh.lz = g.nz;
+    }
+    {
+        const StageShape &s3 = u->shape[3];
+        u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.rows() - 1) / s3.rows()) * ((g.nz + s3.lz - 1) / s3.lz);
+        if ((rc = dev_alloc(ctx, &u->cta_est, (size_t) u->n_tiles3))) return rc;
+        MMF_CUDA(ctx, cudaMemsetAsync(u->cta_est, 0, sizeof(float) * u->n_tiles3, ctx->stream));
+        if ((rc = dev_alloc(ctx, &u->eig_cand, (size_t) u->n_tiles3 + 1))) return rc;
+    }
+    return MMF_OK;
+}
+
 static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
 {
     UniformGeom &g = u->g;
@@ -147,35 +185,9 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
     if (u->bodies) { // a box with bodies: the one kernel form that knows about them, whatever MMF_STAGE_CFG says
         for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'c', 12 };
     }
-    // z chunk per CTA: every CTA holds one SM (1 CTA/SM), so the grid runs in ceil(CTAs/SMs) rounds.
-    // Pick the chunk count whose last round is fullest, charging each chunk the extra plane it
-    // derives for its first z interface; chunks stay between 4 and 96 planes (a small box -- the reference's own 32^3
-    // cases -- fills the SMs only with short chunks: a CTA marches through its planes one after the other, 1.8 us each).
     u->clamp_ff = true;
     u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));
-    const char *env_lz = getenv("MMF_STAGE_LZ");
-    for (int st = 0; st < 4; ++st) {
-        StageShape &sh = u->shape[st];
-        if (env_lz && atoi(env_lz) > 0) { sh.lz = atoi(env_lz); continue; }
-        const long long tiles_xy = (long long) ((g.nx + XW - 1) / XW) * ((g.ny + sh.rows() - 1) / sh.rows());
-        const double sms = (double) ctx->prop.multiProcessorCount;
-        double best = -1.;
-        for (int chunks = std::max(1, (g.nz + 95) / 96); chunks <= std::max(1, g.nz / 4); ++chunks) {
-            const int lz = (g.nz + chunks - 1) / chunks;
-            const long long n_chunks = (g.nz + lz - 1) / lz;
-            const double waves = (double) (tiles_xy * n_chunks) / sms;
-            const double score = waves / std::ceil(waves) * (double) lz / (lz + 1.0);
-            if (score > best + 1e-9) { best = score; sh.lz = lz; }
-        }
-        if (sh.lz <= 0) sh.lz = g.nz;
-    }
-    {
-        const StageShape &s3 = u->shape[3];
-        u->n_tiles3 = ((g.nx + XW - 1) / XW) * ((g.ny + s3.rows() - 1) / s3.rows()) * ((g.nz + s3.lz - 1) / s3.lz);
-        if ((rc = dev_alloc(ctx, &u->cta_est, (size_t) u->n_tiles3))) return rc;
-        MMF_CUDA(ctx, cudaMemsetAsync(u->cta_est, 0, sizeof(float) * u->n_tiles3, ctx->stream));
-        if ((rc = dev_alloc(ctx, &u->eig_cand, (size_t) u->n_tiles3 + 1))) return rc;
-    }
+    if ((rc = uniform_setup_shapes(ctx))) return rc;
     MMF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MMF_OK;
 }
