@@ -253,8 +253,10 @@ int mmf_profile_begin(mmf_ctx *ctx);
 int mmf_profile_end(mmf_ctx *ctx, double total_ms[4], int64_t launches[4]);
 /* Writes a scratch buffer larger than L2 on the handle's stream (L2 flush between timed runs).  */
 int mmf_flush_l2(mmf_ctx *ctx);
-/* GPU self-test of the shared-reciprocal division used by the uniform kernels: counts bitwise
- * mismatches against IEEE `/` over ~n_samples random operand pairs (must be 0). */
+/* GPU self-test of the shared-reciprocal division used by the kernels: counts bitwise mismatches against IEEE `/`
+ * over ~n_samples random operand pairs AND a directed sweep (structured mantissas for numerator and denominator --
+ * all zeros / ones, single bits, ends of the range --, exponents up to 2^+-300 on either side, both signs, products
+ * b*q next to representable quotients, a = +0); must be 0. */
 int mmf_selftest_division(int device, long long n_samples, unsigned long long seed, unsigned long long *mismatches);
 /* Pinned host memory for the e2e leg. */
 int mmf_host_alloc(void **ptr, size_t bytes);

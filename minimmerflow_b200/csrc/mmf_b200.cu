@@ -749,6 +749,7 @@ extern "C" int mmf_selftest_division(int device, long long n_samples, unsigned l
     const int blocks = 148 * 8, threads = 256;
     const long long per_thread = std::max<long long>(1, n_samples / ((long long) blocks * threads));
     division_selftest_kernel<<<blocks, threads>>>(seed, per_thread, d);
+    division_directed_kernel<<<64, 64>>>(d); // structured mantissas x exponent pairs, +-a, products, a = +0
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, sizeof *d, cudaMemcpyDeviceToHost);
     cudaFree(d);

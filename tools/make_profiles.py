@@ -101,10 +101,11 @@ def main():
         text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
         chunks = re.split(r"\n(?=\s*Function : )", text)
         # (ELb0 = padded x ghost columns: the single-GPU instantiation the bench runs)
-        want = {"uniform_stage_kernel_tILi0ELi0ELi16ELi4E": "stage0_rhs_only_t_16warps",
-                "uniform_stage_kernel_tILi1ELi0ELi16ELi4E": "stage1_t_16warps",
-                "uniform_stage_kernel_tILi2ELi0ELi16ELi4E": "stage2_t_16warps",
-                "uniform_stage_kernel_tILi3ELi0ELi16ELi4E": "stage3_t_16warps",
+        want = {"uniform_stage_kernel_tILi0ELi0ELi12ELi4ELb1E": "stage0_rhs_only_h_12warps",
+                "uniform_stage_kernel_tILi1ELi0ELi12ELi4ELb1E": "stage1_h_12warps",
+                "uniform_stage_kernel_tILi2ELi0ELi12ELi4ELb1E": "stage2_h_12warps",
+                "uniform_stage_kernel_tILi3ELi0ELi12ELi4ELb1E": "stage3_h_12warps",
+                "uniform_stage_kernel_tILi2ELi0ELi16ELi4ELb0E": "stage2_t_16warps",
                 # the rotate form (per-thread global loads): what runs when an x side is a partition side
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb0": "stage2_v5r_12warps",
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb1": "stage2_v5r_12warps_xghost",
