@@ -144,8 +144,14 @@ typedef struct mmf_uniform_desc {
     int32_t  cell_numbering;       /* raw cell id <-> lattice coordinate inside the box            */
     int32_t  interface_numbering;  /* decides the per-cell face accumulation order                 */
     int32_t  bc_side[6];           /* MMF_BC_* on the global -x,+x,-y,+y,-z,+z sides               */
-    double   h;                    /* cell size: area = h*h, volume = h*h*h                        */
+    double   h;                    /* cell size                                                    */
     double   dirichlet_info[MMF_N_FIELDS];
+    /* What meshInfo.rawGetInterfaceArea / rawGetCellVolume return for this mesh (src/mesh_info.cpp:86-118).
+     * 0 = built as h*h and h*h*h, which equals a host's own evalInterfaceArea / evalCellVolume only to
+     * the last ulp: a host that wants the bits of ITS geometry passes its two values here.  A caller
+     * compiled against the header without these two fields (struct_size = offset of `area`) gets 0.  */
+    double   area;
+    double   volume;
 } mmf_uniform_desc;
 
 typedef struct mmf_ctx mmf_ctx;

@@ -61,6 +61,8 @@ class UniformDesc(C.Structure):
         ("bc_side", C.c_int32 * 6),
         ("h", C.c_double),
         ("dirichlet_info", C.c_double * N_FIELDS),
+        ("area", C.c_double),
+        ("volume", C.c_double),
     ]
 
 

@@ -10,6 +10,7 @@
 #include "mmf_b200.h"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -108,6 +109,10 @@ inline mmf_ctx *createContext(problem::ProblemType problemType, const MeshGeomet
     if (mmf_create(&desc, device ? std::atoi(device) : 0, &ctx) != MMF_OK) fail("mmf_create", nullptr);
     return ctx;
 }
+
+// solver_b200.cpp: drops the device context of the strict adapters; the next computeRHS / computePolynomials call
+// describes the mesh, the solved flags and the BC table again.  For hosts that edit those tables in place.
+void invalidateContext();
 
 } // namespace mmf_b200
 

@@ -25,19 +25,42 @@ using mmf_b200::fail;
 struct Binding {
     const MeshGeometricalInfo *meshInfo = nullptr;
     std::size_t nCells = 0, nInterfaces = 0;
+    int problemType = -1;
+    std::uint64_t tables = 0; // fingerprint of the solved-flag and BC tables the context was described with
     mmf_ctx *ctx = nullptr;
     ~Binding() { if (ctx) mmf_destroy(ctx); }
 };
 
 Binding g_binding;
 
+// The device context holds a COPY of the solved flags, the BC table and the geometry.  A caller that changes them
+// under the same mesh object (another body, another problem, a mesh adapted back to the same counts) must not be
+// served the stale copy: every call compares a fingerprint of the two tables -- every entry up to 2^16 of them,
+// beyond that an evenly strided sample of 2^16, so that the check stays far below the cost of the call on the
+// large meshes -- and mmf_b200::invalidateContext() drops the context outright (a host that edits single entries
+// of a large table calls it).
+std::uint64_t tableFingerprint(const CellStorageBool &cellSolvedFlag, std::size_t nCells,
+                               const InterfaceStorageInt &interfaceBCs, std::size_t nInterfaces)
+{
+    const std::size_t SAMPLES = std::size_t(1) << 16;
+    std::uint64_t hash = 1469598103934665603ull; // FNV-1a
+    auto mix = [&hash](std::uint64_t v) { hash = (hash ^ v) * 1099511628211ull; };
+    const std::size_t cellStride = nCells > SAMPLES ? nCells / SAMPLES : 1;
+    for (std::size_t i = 0; i < nCells; i += cellStride) mix(cellSolvedFlag.rawAt(i) ? 2 : 1);
+    const std::size_t interfaceStride = nInterfaces > SAMPLES ? nInterfaces / SAMPLES : 1;
+    for (std::size_t i = 0; i < nInterfaces; i += interfaceStride) mix((std::uint64_t) (std::int64_t) interfaceBCs.rawAt(i));
+    return hash;
+}
+
 mmf_ctx *context(problem::ProblemType problemType, const MeshGeometricalInfo &meshInfo,
                  const CellStorageBool &cellSolvedFlag, const InterfaceStorageInt &interfaceBCs)
 {
     Binding &b = g_binding;
     const std::size_t nCells = meshInfo.getCellRawIds().size(), nInterfaces = meshInfo.getInterfaceRawIds().size();
-    if (b.ctx && (b.meshInfo != &meshInfo || b.nCells != nCells || b.nInterfaces != nInterfaces)) {
-        mmf_destroy(b.ctx); // the mesh changed: describe it again
+    const std::uint64_t tables = tableFingerprint(cellSolvedFlag, nCells, interfaceBCs, nInterfaces);
+    if (b.ctx && (b.meshInfo != &meshInfo || b.nCells != nCells || b.nInterfaces != nInterfaces ||
+                  b.problemType != (int) problemType || b.tables != tables)) {
+        mmf_destroy(b.ctx); // the mesh, the problem or its flag / BC tables changed: describe them again
         b.ctx = nullptr;
     }
     if (!b.ctx) {
@@ -45,11 +68,23 @@ mmf_ctx *context(problem::ProblemType problemType, const MeshGeometricalInfo &me
         b.meshInfo = &meshInfo;
         b.nCells = nCells;
         b.nInterfaces = nInterfaces;
+        b.problemType = (int) problemType;
+        b.tables = tables;
     }
     return b.ctx;
 }
 
 } // namespace
+
+namespace mmf_b200 {
+
+void invalidateContext()
+{
+    if (g_binding.ctx) mmf_destroy(g_binding.ctx);
+    g_binding.ctx = nullptr;
+}
+
+} // namespace mmf_b200
 
 namespace reconstruction {
 

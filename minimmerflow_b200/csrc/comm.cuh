@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(256) uniform_push_kernel(const UniformGeom g, 
     }
 }
 
-__global__ void uniform_wait_kernel(const unsigned long long *flags, unsigned int side_mask, unsigned long long seq)
+__global__ void uniform_wait_kernel(const unsigned long long *flags, unsigned int side_mask, unsigned long long seq,
+                                    double *timeouts, unsigned long long timeout_ns)
 {
     const int s = threadIdx.x;
     if (s < 6 && ((side_mask >> s) & 1u)) {
-        const volatile unsigned long long *f = flags + s;
-        while (*f < seq) { }
+        if (!halo_spin(flags + s, seq, timeout_ns)) atomicAdd(timeouts, 1.0);
     }
     __threadfence_system();
 }
@@ -487,7 +487,7 @@ static int comm_uniform_dma_push(mmf_ctx *ctx, double *S, int a, bool defer_wait
     }
     u->arr_seq[a] = seq;
     if (!defer_wait) { // nobody downstream waits in-kernel: block the stream until all neighbours have delivered
-        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
+        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq, &ctx->d_ctl->halo_timeouts, halo_timeout_ns());
         MMF_LAUNCH_CHECK(ctx);
     }
     return MMF_OK;
@@ -544,7 +544,7 @@ static int comm_uniform_push_enqueue(mmf_ctx *ctx, double *S, bool defer_wait)
     }
     u->arr_seq[a] = seq;
     if (!defer_wait) { // nobody downstream waits in-kernel: block the stream until all neighbours have delivered
-        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq);
+        uniform_wait_kernel<<<1, 32, 0, ctx->stream>>>(u->flags, mask, seq, &ctx->d_ctl->halo_timeouts, halo_timeout_ns());
         MMF_LAUNCH_CHECK(ctx);
     }
     return MMF_OK;

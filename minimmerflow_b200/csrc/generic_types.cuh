@@ -38,6 +38,7 @@ struct StepControl {
     double eig_next;
     double est_max;      // largest FP32 eigenvalue estimate over the tiles (all ranks after the all-reduce)
     double mismatches;   // sticky: steps whose dt eigenvalue differed from stage 1's own face maximum
+    double halo_timeouts; // sticky: halo waits that gave up on a neighbour rank's layer (results are then invalid)
 };
 constexpr int STEP_CONTROL_HOST_FIELDS = 7;
 

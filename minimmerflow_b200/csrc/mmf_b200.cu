@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -183,7 +184,8 @@ extern "C" int mmf_create_uniform(const mmf_uniform_desc *desc, int device, mmf_
 {
     if (!out) return fail(nullptr, MMF_ERR_INVALID, "mmf_create_uniform: out is NULL");
     *out = nullptr;
-    if (!desc || desc->struct_size != sizeof(mmf_uniform_desc)) {
+    // (the description grew by `area` and `volume`: a caller built against the shorter struct is still served)
+    if (!desc || (desc->struct_size != sizeof(mmf_uniform_desc) && desc->struct_size != offsetof(mmf_uniform_desc, area))) {
         return fail(nullptr, MMF_ERR_INVALID, "mmf_create_uniform: bad description / ABI mismatch");
     }
     mmf_ctx *ctx = new (std::nothrow) mmf_ctx();
@@ -520,7 +522,15 @@ static int upload_control(mmf_ctx *ctx, double cfl, double min_h, double t, doub
     // (eig_next / eig_seed) stays valid across calls as long as nothing else touched field U
     MMF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ctl, h, STEP_CONTROL_HOST_FIELDS * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     MMF_CUDA(ctx, cudaMemsetAsync(&ctx->d_ctl->mismatches, 0, sizeof(double), ctx->stream));
+    // (halo_timeouts stays: once a neighbour rank failed to deliver, the handle's state is invalid for good)
     return MMF_OK;
+}
+
+static int halo_timeout_error(mmf_ctx *ctx, const char *who)
+{
+    return fail(ctx, MMF_ERR_NCCL, "%s: %d halo wait(s) gave up after %.1f s without a neighbour rank's layer (a rank died or "
+                "fell behind; MMF_HALO_TIMEOUT_MS, 0 = wait for ever): the state of this rank is invalid", who,
+                (int) ctx->h_ctl->halo_timeouts, 1e-9 * (double) halo_timeout_ns());
 }
 
 static int download_control(mmf_ctx *ctx)
@@ -540,6 +550,7 @@ extern "C" int mmf_step(mmf_ctx *ctx, double cfl, double min_cell_size, double t
     if ((rc = step_enqueue(ctx))) return rc;
     ctx->state_valid[MMF_FIELD_W] = ctx->state_valid[MMF_FIELD_RHS] = true;
     if ((rc = download_control(ctx))) return rc;
+    if (ctx->h_ctl->halo_timeouts != 0.0) return halo_timeout_error(ctx, "mmf_step");
     if (ctx->h_ctl->mismatches != 0.0) {
         return fail(ctx, MMF_ERR_STATE, "mmf_step: internal check failed: the max eigenvalue that chose dt (%.17g) is not "
                     "the face maximum of the stage-1 residual (%.17g)", ctx->h_ctl->max_eig[0], ctx->h_ctl->max_eig_chk);
@@ -578,6 +589,7 @@ extern "C" int mmf_run(mmf_ctx *ctx, double cfl, double min_cell_size, double *t
         if (bounded_time && !(ctx->h_ctl->t < t_max)) break;
     }
     ctx->state_valid[MMF_FIELD_W] = ctx->state_valid[MMF_FIELD_RHS] = true;
+    if (ctx->h_ctl->halo_timeouts != 0.0) return halo_timeout_error(ctx, "mmf_run");
     if (ctx->h_ctl->mismatches != 0.0) {
         return fail(ctx, MMF_ERR_STATE, "mmf_run: internal check failed in %d step(s): the max eigenvalue that chose dt "
                     "is not the face maximum of the stage-1 residual", (int) ctx->h_ctl->mismatches);

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,17 @@ struct UniformPath; // uniform_path.cuh
 struct Comm;        // comm.cuh
 
 } // namespace mmf
+
+// how long a halo wait spins for a neighbour rank's layer before it gives up (halo_spin, uniform_device.cuh)
+static inline unsigned long long halo_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char *e = getenv("MMF_HALO_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 30000.0;
+        return (unsigned long long) (ms > 0. ? ms * 1e6 : 0.);
+    }();
+    return ns;
+}
 
 struct mmf_ctx {
     int device = -1;

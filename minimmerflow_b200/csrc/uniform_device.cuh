@@ -43,7 +43,25 @@ struct HaloWait {
     unsigned int mask;               // sides that have a neighbour rank
     const int *tile_order;           // [tx*ty*tz] tile visited by CTA b (1-D grid); nullptr: 3-D grid
     int tx, ty, tz;
+    // a neighbour that died never raises its counter: a waiting thread gives up after timeout_ns (0 = never) and
+    // counts itself in StepControl::halo_timeouts, which the host turns into an error when the call returns
+    double *timeouts;
+    unsigned long long timeout_ns;
 };
+
+// spin until the arrival counter reaches seq; false = gave up
+__device__ __forceinline__ bool halo_spin(const volatile unsigned long long *f, unsigned long long seq, unsigned long long timeout_ns)
+{
+    if (*f >= seq) return true;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+#pragma unroll 1
+        for (int n = 0; n < 256; ++n) {
+            if (*f >= seq) return true;
+        }
+        if (timeout_ns && global_timer_ns() - t0 > timeout_ns) return false;
+    }
+}
 
 // Multi-GPU, direct peer stores: ghost cells across an x partition side live in a COMPACT array
 // [field][k+1][j+1] instead of the padded state array.  In the padded array the x ghost column is one

@@ -159,6 +159,8 @@ static int stage_launch_prelude(mmf_ctx *ctx, int stage, const double *Sin, doub
             hw.flags = u->flags;
             hw.seq = u->arr_seq[ain];
             hw.tile_order = u->tile_order[stage];
+            hw.timeouts = &ctx->d_ctl->halo_timeouts;
+            hw.timeout_ns = halo_timeout_ns();
             if (hw.tile_order) a.grid = dim3(a.grid.x * a.grid.y * a.grid.z, 1, 1);
         }
     }

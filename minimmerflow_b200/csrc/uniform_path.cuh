@@ -220,8 +220,12 @@ static int uniform_create(mmf_ctx *ctx, const mmf_uniform_desc *d)
     g.gx0 = d->box_offset[0]; g.gy0 = d->box_offset[1]; g.gz0 = d->box_offset[2];
     g.gnx = d->global_dims[0]; g.gny = d->global_dims[1]; g.gnz = d->global_dims[2];
     g.h = d->h;
-    g.area = g.h * g.h;
-    g.volume = g.h * g.h * g.h;
+    const bool has_geom = d->struct_size >= sizeof(mmf_uniform_desc);
+    if (has_geom && (d->area < 0. || d->volume < 0. || (d->area > 0.) != (d->volume > 0.))) {
+        return fail(ctx, MMF_ERR_INVALID, "mmf_create_uniform: area and volume must both be given (> 0) or both be 0");
+    }
+    g.area = (has_geom && d->area > 0.) ? d->area : g.h * g.h;           // the host's own values verbatim, if it passes them
+    g.volume = (has_geom && d->volume > 0.) ? d->volume : g.h * g.h * g.h;
     for (int s = 0; s < 6; ++s) {
         const int axis = s >> 1;
         const bool hi = s & 1;

@@ -124,8 +124,7 @@ __device__ __forceinline__ void halo_wait(const HaloWait &hw, const TileId &t)
     if (t.bz == hw.tz - 1) touched |= 32u;
     const unsigned int need = touched & hw.mask;
     if (need && threadIdx.x < 6 && ((need >> threadIdx.x) & 1u)) {
-        const volatile unsigned long long *f = hw.flags + threadIdx.x;
-        while (*f < hw.seq) { }
+        if (!halo_spin(hw.flags + threadIdx.x, hw.seq, hw.timeout_ns)) atomicAdd(hw.timeouts, 1.0);
         __threadfence_system();
     }
 }

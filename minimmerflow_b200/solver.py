@@ -99,8 +99,9 @@ class EulerSolver:
     @classmethod
     def uniform(cls, box_dims, h, bc_side, device=0, flags=0, problem_type=0,
                 cell_numbering=A.NUMBERING_MORTON, interface_numbering=A.NUMBERING_MORTON,
-                global_dims=None, box_offset=(0, 0, 0), dirichlet_info=None):
-        """Full uniform 3-D box from the compact description (mmf_create_uniform)."""
+                global_dims=None, box_offset=(0, 0, 0), dirichlet_info=None, area=0.0, volume=0.0):
+        """Full uniform 3-D box from the compact description (mmf_create_uniform).  area / volume: the host's own
+        interface area and cell volume (0 = h*h and h*h*h)."""
         lib = A.load_library()
         d = A.UniformDesc()
         d.struct_size = C.sizeof(A.UniformDesc)
@@ -116,6 +117,8 @@ class EulerSolver:
         for s in range(6):
             d.bc_side[s] = int(bc_side[s])
         d.h = float(h)
+        d.area = float(area)
+        d.volume = float(volume)
         if dirichlet_info is not None:
             for k in range(A.N_FIELDS):
                 d.dirichlet_info[k] = float(dirichlet_info[k])

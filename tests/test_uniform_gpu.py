@@ -212,6 +212,33 @@ def test_compact_descriptor_equals_full_descriptor(mmf, oracle):
         assert bits_equal(a.get_state(mmf.FIELD_U), b.get_state(mmf.FIELD_U))
 
 
+def test_compact_descriptor_takes_host_area_and_volume(mmf, oracle):
+    """The compact description builds area = h*h and volume = h*h*h unless the host passes ITS values
+    (mmf_uniform_desc.area / .volume): values one ulp away from the products must be used verbatim, like the
+    tables of a full description (src/mesh_info.cpp:86-118 caches whatever the mesh evaluates)."""
+    m = oracle.problem_mesh("radsod", 3, 16)
+    h = m["h"]
+    A, V = np.nextafter(h * h, 1.0), np.nextafter(h * h * h, 0.0)
+    m["area"] = np.full_like(m["area"], A)
+    m["volume"] = np.full_like(m["volume"], V)
+    U = oracle.init_state(m)
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    t = 0.0
+    for _ in range(4):
+        dto, _ = oracle.step(m, 0.45, t, 1e30, Uo, Wo, Ro)
+        t += dto
+    with mmf.EulerSolver.uniform((16, 16, 16), h, _bc_sides(m), area=A, volume=V) as b, \
+            mmf.EulerSolver.uniform((16, 16, 16), h, _bc_sides(m)) as c:
+        b.set_state(mmf.FIELD_U, U)
+        c.set_state(mmf.FIELD_U, U)
+        assert b.run(0.45, h, 0.0, 1e30, max_steps=4) == (t, 4)
+        c.run(0.45, h, 0.0, 1e30, max_steps=4)
+        assert bits_equal(b.get_state(mmf.FIELD_U), Uo)
+        assert not bits_equal(c.get_state(mmf.FIELD_U), Uo)  # the products differ by an ulp, and it shows
+    with pytest.raises(mmf.MmfError):
+        mmf.EulerSolver.uniform((16, 16, 16), h, _bc_sides(m), area=A)  # one of the two only
+
+
 def test_lexicographic_numbering_non_cubic_box(mmf, oracle):
     """Non-cubic, non-power-of-two box numbered lexicographically: uniform path must detect the
     numbering and stay bit-exact; ragged tiles in x (37 = 30 + 7) and y."""
