@@ -4,7 +4,7 @@
 //   r = the rotate form (uniform_stage_v5r.cuh), the default of every stage
 //   c = the rotate form for a box with bodies (uniform_stage_v5rb.cuh), wall cells by a small pass around it
 //   t = the same scheme with its input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh);
-//       also serves form 'h' (one warp for both halo rows)
+//       also serves form 'h' (one warp for both halo rows) and form 'b' (form 'h' for a box with bodies)
 #include "uniform_launch.cuh"
 
 #ifndef MMF_TU_FORM_ID // a bare `nvcc -c stage_tu.cu` (no Makefile): the rotate form, RHS only
@@ -18,13 +18,42 @@
 #elif MMF_TU_FORM_ID == 1
 #include "uniform_stage_v5rb.cuh"
 #elif MMF_TU_FORM_ID == 2
-#include "uniform_stage_v5r.cuh"
+#include "uniform_stage_v5rb.cuh" // (the wall-cell kernels around form 'b')
 #include "uniform_stage_t.cuh"
 #else
 #error "MMF_TU_FORM_ID must be 0 (r), 1 (c) or 2 (t)"
 #endif
 
 namespace mmf {
+
+#if MMF_TU_FORM_ID == 1 || MMF_TU_FORM_ID == 2
+// a box with bodies (forms 'b' and 'c'): the wall cells' results into the compact buffer BEFORE the stage kernel runs
+// (it does not store them, and stage 3 updates U in place), and from the buffer into the output array behind it
+template <int STAGE, int ORDER>
+static int launch_wall_cells(mmf_ctx *ctx, const double *Sin, const double *Un, double *d_max)
+{
+    UniformPath *u = ctx->uni;
+    if (!u->solid || !u->wall_list || !u->wall_compact) return fail(ctx, MMF_ERR_INVALID, "the stage kernels for a box with bodies need the flag array and the wall-cell list");
+    if (u->n_wall > 0) {
+        uniform_wall_cells_kernel<STAGE, ORDER><<<(u->n_wall + 127) / 128, 128, 0, ctx->stream>>>(
+            u->g, uniform_load_clamp(u), Sin, Un, u->solid, u->wall_list, u->n_wall, ctx->d_ctl, u->wall_compact, d_max);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
+}
+
+template <int STAGE>
+static int launch_wall_scatter(mmf_ctx *ctx, double *Out)
+{
+    UniformPath *u = ctx->uni;
+    if (u->n_wall > 0) {
+        uniform_wall_scatter_kernel<<<(u->n_wall + 127) / 128, 128, 0, ctx->stream>>>(u->g.fs, u->wall_list, u->n_wall,
+                                                                                      u->wall_compact, Out, ctx->d_ctl, STAGE >= 1);
+        MMF_LAUNCH_CHECK(ctx);
+    }
+    return MMF_OK;
+}
+#endif
 
 template <int STAGE, int ORDER>
 static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, double *Out, double *d_max)
@@ -33,24 +62,20 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
     const StageShape sh = u->shape[STAGE];
 #if MMF_TU_FORM_ID == 1
     (void) sh;
-    // wall cells into the compact buffer, the stage kernel (which does not store them), the buffer into the output
-    if (!u->wall_list || !u->wall_compact) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'c' needs the wall-cell list");
-    if (u->n_wall > 0) {
-        uniform_wall_cells_kernel<STAGE, ORDER><<<(u->n_wall + 127) / 128, 128, 0, ctx->stream>>>(
-            u->g, uniform_load_clamp(u), Sin, Un, u->solid, u->wall_list, u->n_wall, ctx->d_ctl, u->wall_compact, d_max);
-        MMF_LAUNCH_CHECK(ctx);
-    }
+    if (int rc = launch_wall_cells<STAGE, ORDER>(ctx, Sin, Un, d_max)) return rc;
     if (int rc = launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12, true>, STAGE, Sin, Un, Out, d_max)) return rc;
-    if (u->n_wall > 0) {
-        uniform_wall_scatter_kernel<<<(u->n_wall + 127) / 128, 128, 0, ctx->stream>>>(u->g.fs, u->wall_list, u->n_wall,
-                                                                                      u->wall_compact, Out, ctx->d_ctl, STAGE >= 1);
-        MMF_LAUNCH_CHECK(ctx);
-    }
-    return MMF_OK;
+    return launch_wall_scatter<STAGE>(ctx, Out);
 #elif MMF_TU_FORM_ID == 2
     // (compact x ghost columns -- an x partition side -- are only read by the rotate form: comm_ipc_import switches the
     //  stages' shapes to it)
     if (uniform_use_xghost(ctx)) return fail(ctx, MMF_ERR_STATE, "stage-kernel forms 't' / 'h' cannot read compact x ghost columns");
+    if (sh.form == 'b') {
+        if (int rc = launch_wall_cells<STAGE, ORDER>(ctx, Sin, Un, d_max)) return rc;
+        if (int rc = launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, 12, T_DEPTH, true, true>, STAGE, 12, true,
+                                     stage_t_smem_bytes(12, STAGE, T_DEPTH, true), Sin, Un, Out, d_max, u->solid)) return rc;
+        return launch_wall_scatter<STAGE>(ctx, Out);
+    }
+    if (u->bodies) return fail(ctx, MMF_ERR_STATE, "a box with bodies runs kernel form 'b' or 'c'");
 #define MMF_LAUNCH_T(NWV, DV, MHV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV, MHV>, STAGE, NWV, MHV, stage_t_smem_bytes(NWV, STAGE, DV, MHV), Sin, Un, Out, d_max)
     if (sh.form == 'h') { if (sh.nw == 12) MMF_LAUNCH_T(12, T_DEPTH, true); MMF_LAUNCH_T(16, T_DEPTH, true); }
     if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH, false);

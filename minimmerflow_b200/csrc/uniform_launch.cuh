@@ -17,13 +17,14 @@ namespace mmf {
 //   'r' the rotate form of the low-face streaming kernel (uniform_stage_v5r.cuh), the default: 12 warps
 //   't' the same scheme with the input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh)
 //   'h' form 't' with ONE warp serving both halo rows of the tile: nw - 1 update rows per CTA
-//   'c' the rotate form for a box WITH BODIES (uniform_stage_v5rb.cuh, 12 warps; chosen by the path itself, never
-//       by MMF_STAGE_CFG), the wall cells recomputed by a small pass around the stage kernel
+//   'b' form 'h' for a box WITH BODIES (12 warps; chosen by the path itself, never by MMF_STAGE_CFG): one flag byte per
+//       cell, the wall cells recomputed by a small pass around the stage kernel
+//   'c' the rotate form for a box with bodies (uniform_stage_v5rb.cuh, 12 warps; MMF_UNIFORM_BODIES=2), likewise
 struct StageShape {
     char form = 'r';
     int nw = 12;
     int lz = 0; // planes per CTA
-    int rows() const { return form == 'h' ? nw - 1 : nw - 2; } // y rows a CTA updates: all warps but the halo warp(s)
+    int rows() const { return (form == 'h' || form == 'b') ? nw - 1 : nw - 2; } // y rows a CTA updates: all warps but the halo warp(s)
     StageShape() = default;
     StageShape(char f, int n) : form(f), nw(n) {}
 };
@@ -242,7 +243,7 @@ static int uniform_in_map(mmf_ctx *ctx, const double *arr, int rows, const TmaDe
 
 template <typename K>
 static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, bool merged_halo, size_t smem, const double *Sin, const double *Un,
-                           double *Out, double *d_max)
+                           double *Out, double *d_max, const unsigned char *solid = nullptr)
 {
     UniformPath *u = ctx->uni;
     const int nu = merged_halo ? nw - 1 : nw - 2; // update rows, tile rows = nu + 2
@@ -258,7 +259,7 @@ static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, bool merged_
     {
         ScopedLaunchTimer timer(ctx, stage);
         kern<<<a.grid, nw * 32, smem, ctx->stream>>>(u->g, Out, ctx->d_ctl, d_max, u->shape[stage].lz,
-                                                     (stage == 3) ? u->cta_est : nullptr, uniform_load_clamp(u), a.hw, sm, um);
+                                                     (stage == 3) ? u->cta_est : nullptr, uniform_load_clamp(u), a.hw, sm, um, solid);
     }
     MMF_LAUNCH_CHECK(ctx);
     return MMF_OK;
@@ -302,7 +303,7 @@ MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_t.cuh: input staged by bulk tensor loads
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('r', 'c', 't' / 'h') for a stage
+// the launcher of a kernel form ('r', 'c', 't' / 'h' / 'b') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
     static const StageLauncher tab[3][4] = {
@@ -310,7 +311,7 @@ inline StageLauncher stage_launcher(char form, int stage)
         { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
     };
-    return tab[(form == 'c') ? 1 : (form == 't' || form == 'h') ? 2 : 0][stage];
+    return tab[(form == 'c') ? 1 : (form == 't' || form == 'h' || form == 'b') ? 2 : 0][stage];
 }
 
 } // namespace mmf

@@ -97,7 +97,7 @@ static int uniform_refresh_ghosts(mmf_ctx *ctx, double *S, int check_active, dou
     if (any) {
         const int na = std::max(g.nx, g.ny), nb = std::max(g.ny, g.nz);
         dim3 grid((na + 255) / 256, nb, 6);
-        uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next, skip_ff);
+        uniform_ghost_kernel<<<grid, 256, 0, ctx->stream>>>(g, S, ctx->d_ctl, check_active, eig_next, skip_ff, ctx->uni->solid);
         MMF_LAUNCH_CHECK(ctx);
     }
     trace_point(ctx, "bc");
@@ -182,8 +182,11 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
             if (last) { for (; st < 4; ++st) u->shape[st] = sh; } // one entry = all stages
         }
     }
-    if (u->bodies) { // a box with bodies: the one kernel form that knows about them, whatever MMF_STAGE_CFG says
-        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'c', 12 };
+    if (u->bodies) {
+        // a box with bodies: the kernel forms that know about them, whatever MMF_STAGE_CFG says -- 'b', the TMA-fed kernel
+        // with one warp for both halo rows plus the flag array; MMF_UNIFORM_BODIES=2: 'c', the rotate form plus the flag
+        const bool rotate = getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) == 2;
+        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ rotate ? 'c' : 'b', 12 };
     }
     u->clamp_ff = true;
     u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));
@@ -390,14 +393,14 @@ static int uniform_step_enqueue(mmf_ctx *ctx)
     double *U = u->arr[0], *Wa = u->arr[1], *Wb = u->arr[2];
 
     trace_point(ctx, "gap");
-    if (u->eig_candidate && !u->bodies) {
+    if (u->eig_candidate) {
         // steady state: eig_next was found (and reduced over the ranks) at the end of the previous step
         begin_step_choose_dt_kernel<<<1, 1, 0, ctx->stream>>>(c);
         MMF_LAUNCH_CHECK(ctx);
     } else {
         begin_step_kernel<<<1, 1, 0, ctx->stream>>>(c, 0);
         MMF_LAUNCH_CHECK(ctx);
-        if (u->bodies) { // a box with bodies: a full pass every step (wall images have their own eigenvalue)
+        if (u->bodies) { // a box with bodies: fluid cells, border ghosts behind them, wall images
             dim3 grid((g.nx + 255) / 256, g.ny, g.nz);
             uniform_eig_body_kernel<<<grid, 256, 0, ctx->stream>>>(g, U, u->solid, &c->max_eig[0]);
             MMF_LAUNCH_CHECK(ctx);
@@ -427,7 +430,7 @@ static int uniform_step_enqueue(mmf_ctx *ctx)
     trace_point(ctx, "stage3");
     u->w_cur = 2;
     const StageShape &s3 = u->shape[3];
-    if (!u->bodies) {
+    {
         // ghost cells of a non-copy boundary condition add their own eigenvalue, then the listed tiles
         if ((rc = uniform_refresh_ghosts(ctx, U, 1, &c->eig_next))) return rc;
         const int tx = (g.nx + XW - 1) / XW, ty = (g.ny + s3.rows() - 1) / s3.rows();
@@ -445,12 +448,16 @@ static int uniform_step_enqueue(mmf_ctx *ctx)
             MMF_LAUNCH_CHECK(ctx);
         }
         uniform_eig_tiles_kernel<<<4 * ctx->prop.multiProcessorCount, 320, 0, ctx->stream>>>(g, U, u->eig_cand, tx, ty, s3.rows(),
-                                                                                             s3.lz, &c->eig_next);
+                                                                                             s3.lz, &c->eig_next, u->solid);
         MMF_LAUNCH_CHECK(ctx);
+        if (u->bodies && u->n_wall > 0) {
+            // the cells that touch a wall are neither stored nor estimated by the stage kernel, and a wall's mirror image
+            // has its own eigenvalue: a pass over the wall-cell list (a surface)
+            uniform_eig_wall_kernel<<<(u->n_wall + 127) / 128, 128, 0, ctx->stream>>>(g, U, u->solid, u->wall_list, u->n_wall, c, &c->eig_next);
+            MMF_LAUNCH_CHECK(ctx);
+        }
         u->eig_candidate = true;
         trace_point(ctx, "halo3+eig");
-    } else {
-        if ((rc = uniform_refresh_ghosts(ctx, U, 1))) return rc;
     }
     // one message per step: the two values main.cpp only logs (:436, :472), the stage-1 check value
     // and the next step's max eigenvalue (max_eig[1], max_eig[2], max_eig_chk, eig_next are contiguous)
@@ -470,7 +477,7 @@ static int uniform_step(mmf_ctx *ctx)
 {
     UniformPath *u = ctx->uni;
     static const bool graphs_on = !(getenv("MMF_STEP_GRAPH") && atoi(getenv("MMF_STEP_GRAPH")) == 0);
-    const bool steady = graphs_on && u->eig_candidate && !u->bodies && !ctx->comm && !ctx->profiling && !ctx->tracing && u->w_cur == 2;
+    const bool steady = graphs_on && u->eig_candidate && !ctx->comm && !ctx->profiling && !ctx->tracing && u->w_cur == 2;
     if (!steady) return uniform_step_enqueue(ctx);
     if (!u->step_graph) {
         const int64_t launches0 = ctx->kernel_launches;

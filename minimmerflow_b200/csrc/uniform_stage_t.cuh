@@ -21,6 +21,14 @@
 // Arithmetic per value: the same helpers in the same order as every other form, so the results are bit-identical.
 //
 // Not here: compact x ghost columns (XGhost: partition sides across x).  Such launches keep the rotate form.
+//
+// BODY = true (kernel form 'b'): the same kernel for a uniform box WITH BODIES, by the scheme uniform_stage_v5rb.cuh
+// explains -- one flag byte per padded cell (1 = not solved, 2 = fluid cell with a wall interface); a cell that is not
+// solved reports a NEGATIVE max eigenvalue in its x / y / z record (the sign bit is set: a negative value never raises a
+// maximum, and max(lam_fluid, negative) = lam_fluid is in the true maximum anyway), a wall is evaluated like any
+// interface, flagged cells are not stored and the wall cells -- a surface -- are recomputed reference-shaped around the
+// kernel (uniform_wall_cells_kernel / uniform_wall_scatter_kernel).  The flag is a per-thread one-byte global load,
+// one plane ahead: a bulk tensor copy of bytes would need x windows that start on 16-byte boundaries.
 #pragma once
 
 #include "uniform_stage_v5.cuh"
@@ -57,6 +65,12 @@ __host__ __device__ constexpr int t_unroll(int nw) { return MMF_T_UNROLL > 0 ? M
 #define MMF_T_EARLY_RELEASE 1
 #endif
 
+// the NEXT plane's cell is read and derived (primitives, sound speed: one long dependency chain) inside the step of
+// the current plane, whose interface fluxes have the independent work to hide it behind
+#ifndef MMF_T_PIPE
+#define MMF_T_PIPE 0
+#endif
+
 // Rows of a CTA's tile.  Two halo warps (MH = false): warps 0 and NW-1 serve the low and the high halo row, NW-2 warps
 // update.  Merged halo warp (MH = true): warp 0 serves BOTH halo rows -- it publishes the record of the row below the
 // tile and turns the record of the tile's top row into that row's -y_hi; together that is 175 FP64 instructions per
@@ -76,11 +90,18 @@ __host__ __device__ constexpr size_t stage_t_smem_bytes(int nw, int stage, int d
            (size_t) (2 * depth + 2 * t_tile_rows(nw, mh)) * sizeof(unsigned long long);
 }
 
-template <int STAGE, int ORDER, int NW, int D, bool MH>
+// (BODY) the sign bit of a max eigenvalue marks a cell that is not solved: flag 1 -> bit 31 of the high word
+__device__ __forceinline__ double body_mark(const double lam, const unsigned flag)
+{
+    return __hiloint2double(__double2hiint(lam) | (int) (flag << 31), __double2loint(lam));
+}
+
+template <int STAGE, int ORDER, int NW, int D, bool MH, bool BODY = false>
 __global__ void __maxnreg__(stage_regs(NW))
 uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__restrict__ ctl, double *__restrict__ max_eig,
                        const int lz, float *__restrict__ cta_est, const LoadClamp lc, const HaloWait hw,
-                       const __grid_constant__ TmaDesc smap, const __grid_constant__ TmaDesc umap)
+                       const __grid_constant__ TmaDesc smap, const __grid_constant__ TmaDesc umap,
+                       const unsigned char *__restrict__ solid = nullptr)
 {
     extern __shared__ double smem[]; // (no static shared memory: the dynamic window starts 1 KB aligned)
     constexpr int NU = t_update_rows(NW, MH), NR = t_tile_rows(NW, MH); // rows the CTA updates / rows of its tile
@@ -135,6 +156,12 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
     const int own_hi = (min(max(j_hi, lc.jlo), lc.jhi) - j0) * 32 + cx;
     const int dn_hi  = (min(max(j_hi - 1, lc.jlo), lc.jhi) - j0) * 32 + cx;
 
+    // (BODY) flag of this lane's (clamped) cell: the flag array has the layout of one field, its ghost shell repeats the
+    // flag of the cell it touches, so the plane coordinate needs no clamp.  Offsets of plane z0-1 (ring step 0).
+    const int mplane = g.py * g.px;
+    int moff    = BODY ? z0 * mplane + (j0 + ry + 1) * g.px + (i0 + cx + XOFF) : 0;
+    int moff_hi = BODY ? z0 * mplane + (own_hi / 32 + j0 + 1) * g.px + (i0 + cx + XOFF) : 0; // (the high halo row's cell)
+
     const double Ah = 0.5 * g.area;
     DivConsts dc;
     dc.y_gm1 = rcp_nr(GM1);
@@ -146,7 +173,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
 
     // ---- the high halo row's step: the y face (j-1 | j) between the tile's top row and the row above it -----------
     double lmy_hi = 0.0;
-    auto high_halo_step = [&](const int s) {
+    auto high_halo_step = [&](const int s, const unsigned csol_hi) {
         const double *ts = ring + (s % D) * SLOT;
         const double *r_dn = sm_r + (NR - 2) * 6 * 32 + lane;
         double *f = sm_f + (NR - 1) * NF * 32 + lane;
@@ -157,6 +184,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
         derive_cell(cU, dc, q);
         double cFy[NF], cly;
         axis_flux<1>(q, cFy, cly);
+        if (BODY) cly = body_mark(cly, csol_hi);
         double lU[NF], lF[NF], AFy[NF];
 #pragma unroll
         for (int k = 0; k < NF; ++k) lU[k] = ts[k * FSTR + dn_hi];
@@ -197,6 +225,8 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             for (int p = 0; p <= min(D - 1, nsteps + 1); ++p) produce(p);
         }
         double *r = sm_r + lane;
+        unsigned nsol = 0, nsol_hi = 0; // (BODY) flags of the next step's cells
+        if (BODY) { moff += mplane; moff_hi += mplane; nsol = solid[moff]; if (MH) nsol_hi = solid[moff_hi]; }
         for (int s = 1; s <= nsteps; ++s) {
             mbar_arrive_elect(&empty[(s - 1) % D], lane); // this row never reads a slot after its own step
             mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
@@ -204,16 +234,19 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             double cU[NF];
 #pragma unroll
             for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR];
+            const unsigned csol = nsol, csol_hi = nsol_hi;
+            if (BODY && s < nsteps) { moff += mplane; moff_hi += mplane; nsol = solid[moff]; if (MH) nsol_hi = solid[moff_hi]; }
             CellPrim q;
             derive_cell(cU, dc, q);
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
+            if (BODY) cly = body_mark(cly, csol);
             if (s > 1) mbar_wait(&barF[1], (unsigned) ((s - 2) & 1)); // row 1 is done with the previous record
 #pragma unroll
             for (int k = 0; k < NF; ++k) r[k * 32] = cFy[k];
             r[NF * 32] = cly;
             mbar_arrive_elect(&barD[0], lane);
-            if (MH) high_halo_step(s);
+            if (MH) high_halo_step(s, csol_hi);
             if (lane == 0 && s + D - 1 <= nsteps + 1) produce(s + D - 1);
         }
         if (MH) lmax = yf_ok_hi ? lmy_hi : 0.0;
@@ -222,7 +255,9 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
         for (int s = 1; s <= nsteps; ++s) {
             mbar_arrive_elect(&empty[(s - 1) % D], lane);
             mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
-            high_halo_step(s);
+            unsigned csol_hi = 0;
+            if (BODY) { moff_hi += mplane; csol_hi = solid[moff_hi]; }
+            high_halo_step(s, csol_hi);
         }
         lmax = yf_ok_hi ? lmy_hi : 0.0;
     } else {
@@ -250,6 +285,10 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
         double pUc[NF]; // (CARRY only)
         double lmx = 0.0, lmy = 0.0, lmz = 0.0;
         const int xl_idx = min(max(min(max(i - 1, lc.ilo), lc.ihi) - i0, 0), 31) + ry * 32; // the left x neighbour's cell in a slot
+        // (BODY) nsol: flag of the next step's cell, loaded a step ahead; pflag: of the previous step's (it is stored
+        // only if that is 0)
+        unsigned nsol = 0, pflag = 0;
+        if (BODY) { pflag = solid[moff]; moff += mplane; nsol = solid[moff]; }
         // ---- step 0: plane z0-1 only provides the low side of the first z interface ------------------
         {
             mbar_wait(&full[0], 0u);
@@ -260,10 +299,19 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             CellPrim q;
             derive_cell(c0, dc, q);
             axis_flux<2>(q, pFz, plz);
+            if (BODY) plz = body_mark(plz, pflag);
 #pragma unroll
             for (int k = 0; k < NF; ++k) pS[k] = 0.0;
 #pragma unroll
             for (int k = 0; k < NF; ++k) pUc[k] = c0[k];
+        }
+        double nU[NF]; // (MMF_T_PIPE) the next plane's cell and its derived state
+        CellPrim nq;
+        if (MMF_T_PIPE) {
+            mbar_wait(&full[1 % D], (unsigned) ((1 / D) & 1));
+#pragma unroll
+            for (int k = 0; k < NF; ++k) nU[k] = ring[(1 % D) * SLOT + k * FSTR + own];
+            derive_cell(nU, dc, nq);
         }
 
 #pragma unroll UNROLL
@@ -272,17 +320,31 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             const unsigned par = (unsigned) ((s - 1) & 1);
             const double *ts = ring + (s % D) * SLOT;       // this plane
             const double *tp = ring + ((s - 1) % D) * SLOT; // the previous plane
-            mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
             double cU[NF];
-#pragma unroll
-            for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own];
-
             CellPrim q;
-            derive_cell(cU, dc, q);
+            if (MMF_T_PIPE) {
+                // plane s was read and derived during step s-1; now plane s+1 (it exists: the ring runs to step nsteps+1)
+                mbar_wait(&full[(s + 1) % D], (unsigned) (((s + 1) / D) & 1));
+#pragma unroll
+                for (int k = 0; k < NF; ++k) cU[k] = nU[k];
+                q = nq;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) nU[k] = ring[((s + 1) % D) * SLOT + k * FSTR + own];
+                derive_cell(nU, dc, nq);
+            } else {
+                mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
+#pragma unroll
+                for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own];
+            }
+            const unsigned csol = nsol;
+            if (BODY) { moff += mplane; nsol = solid[moff]; } // plane z0+s: at most the ghost plane nz
+
+            if (!MMF_T_PIPE) derive_cell(cU, dc, q);
 
             // ---- y record for row+1 (the earlier it is out, the less row+1 waits) ---------------------
             double cFy[NF], cly;
             axis_flux<1>(q, cFy, cly);
+            if (BODY) cly = body_mark(cly, csol);
 #pragma unroll
             for (int k = 0; k < NF; ++k) r_own[k * 32] = cFy[k];
             r_own[NF * 32] = cly;
@@ -291,6 +353,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             // ---- z interface (kz-1 | kz): completes plane kz-1 ----------------------------------------
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
+            if (BODY) clz = body_mark(clz, csol);
             {
                 double pU[NF], pUn[NF];
 #pragma unroll
@@ -301,7 +364,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
 #pragma unroll
                     for (int k = 0; k < NF; ++k) pUn[k] = tp[SIN + k * UFSTR + un_own];
                 }
-                finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && s > 1, est_max);
+                finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && s > 1 && (!BODY || pflag == 0), est_max);
                 op += plane;
                 if (MMF_T_EARLY_RELEASE) mbar_arrive_elect(&empty[(s - 1) % D], lane); // the previous plane's slot is no longer read by this warp
             }
@@ -311,6 +374,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             {
                 double cFx[NF], clx, lU[NF], lF[NF];
                 axis_flux<0>(q, cFx, clx);
+                if (BODY) clx = body_mark(clx, csol);
 #pragma unroll
                 for (int k = 0; k < NF; ++k) { lU[k] = MMF_T_XLDS ? ts[k * FSTR + xl_idx] : shfl_up_d(cU[k]); lF[k] = shfl_up_d(cFx[k]); }
                 const double ll  = shfl_up_d(clx);
@@ -401,6 +465,7 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
 #pragma unroll
             for (int k = 0; k < NF; ++k) { pS[k] = S[k]; pFz[k] = cFz[k]; }
             plz = clz;
+            if (BODY) pflag = csol;
             if (CARRY) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pUc[k] = cU[k];
@@ -413,21 +478,22 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             const int s = nsteps + 1;
             const double *ts = ring + (s % D) * SLOT;
             const double *tp = ring + ((s - 1) % D) * SLOT;
-            mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
+            if (!MMF_T_PIPE) mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
             double cU[NF], pU[NF], pUn[NF];
 #pragma unroll
-            for (int k = 0; k < NF; ++k) { cU[k] = ts[k * FSTR + own]; pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own]; }
+            for (int k = 0; k < NF; ++k) { cU[k] = MMF_T_PIPE ? nU[k] : ts[k * FSTR + own]; pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own]; }
             CellPrim q;
-            derive_cell(cU, dc, q);
+            if (MMF_T_PIPE) q = nq; else derive_cell(cU, dc, q);
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
+            if (BODY) clz = body_mark(clz, nsol);
             const double lam = llf_area_flux(pU, pFz, plz, cU, cFz, clz, Ah, AFz);
             lmz = (lam < lmz) ? lmz : lam;
             if (STAGE >= 2) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pUn[k] = tp[SIN + k * UFSTR + un_own];
             }
-            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd, est_max);
+            finish_plane<STAGE>(pS, AFz, pU, pUn, dt, g.volume, dc.y_vol, op, fs, upd && (!BODY || pflag == 0), est_max);
         }
         lmax = xf_ok ? lmx : 0.0;
         if (yf_ok) lmax = (lmy < lmax) ? lmax : lmy;

@@ -96,11 +96,12 @@ def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
     assert np.array_equal(box.gather(R), ref)
 
 
-@pytest.mark.parametrize("form", ["c"])
+@pytest.mark.parametrize("form", ["c", "b"])
 @pytest.mark.parametrize("chaos", [0, 300])
 def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, chaos, form):
-    """Kernel form 'c' (uniform_stage_v5rb.cuh; wall cells recomputed by wall_cell_update around a stage kernel
-    without a slow path): a uniform box with bodies -- unsolved cells, wall interfaces
+    """Kernel forms 'c' (uniform_stage_v5rb.cuh) and 'b' (uniform_stage_t.cuh with BODY: the TMA-fed kernel; the
+    default), wall cells recomputed by wall_cell_update around a stage kernel without a slow path: a uniform box
+    with bodies -- unsolved cells, wall interfaces
     evaluated against the fluid cell's mirror image, solid | solid interfaces skipped -- and the eigenvalue
     pass that chooses dt there (eig_body_cell), bit for bit against the oracle."""
     # the reference's set-up: Morton cube, reflecting borders, a box body inside
@@ -117,17 +118,17 @@ def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, ch
     # reflecting borders with a body on them
     m = with_bodies(lexicographic_box_mesh(7, 23, 4, 0.5, 1), [[-1, 4.1, -1, 1.4, 6.4, 9.0], [2.1, 10.1, 0.6, 2.9, 11.4, 1.4]])
     m["problem"] = "radsod"
-    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, form, 8, 3, 2, chaos, 3)
+    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, form, 8 if form == "c" else 12, 3, 2, chaos, 3)
 
 
 BODY_CASES_3D = [c for c in reference_cases() if c["dim"] == 3 and c.get("bodies")]
 
 
-@pytest.mark.parametrize("form", ["c"])
+@pytest.mark.parametrize("form", ["c", "b"])
 @pytest.mark.parametrize("case", BODY_CASES_3D, ids=lambda c: c["name"])
 def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case, form):
     """The whole run of a reference case with bodies -- dt from the eigenvalue pass (eig_body_cell), three fused
-    stages of kernel form 'b' per step, `while (t < tMax)` with the clamp -- driven from the emulator alone and
+    stages of a body kernel form per step, `while (t < tMax)` with the clamp -- driven from the emulator alone and
     compared with the final fields the UNMODIFIED reference wrote (tests/golden/reference_fields.npz)."""
     ref = reference_fields()
     n = case["name"]

@@ -123,11 +123,17 @@ def _body_meshes(oracle):
     yield "box 37x29x11 + bodies", m
 
 
-def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
-    """Kernel form 'c' (uniform_stage_v5rb.cuh + wall_cell_update): a uniform box with bodies takes the fused path by
-    itself -- RHS, the dt eigenvalue, ten fused steps and the unfused operator sequence, bitwise against the oracle;
-    cells that are not solved keep the host's values."""
-    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
+@pytest.mark.parametrize("form", ["b", "c"])
+def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch, form):
+    """Kernel forms 'b' (the default: the TMA-fed kernel with the flag array, uniform_stage_t.cuh BODY) and 'c'
+    (MMF_UNIFORM_BODIES=2: the rotate form with it, uniform_stage_v5rb.cuh), both + wall_cell_update: a uniform box with
+    bodies takes the fused path by itself -- RHS, the dt eigenvalue (full pass at the first step, then from the stage-3
+    tile estimates, the wall cells and the border ghosts), ten fused steps and the unfused operator sequence, bitwise
+    against the oracle; cells that are not solved keep the host's values."""
+    if form == "b":
+        monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
+    else:
+        monkeypatch.setenv("MMF_UNIFORM_BODIES", "2")
     rng = np.random.default_rng(11)
     for name, m in _body_meshes(oracle):
         nc = m["volume"].shape[0]
@@ -162,6 +168,33 @@ def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
             assert s.compute_rhs(mmf.FIELD_W) == me, name
             oracle.rk_stage(m, 2, dt, Uo, Wo, R); s.rk_stage(2, dt)
             assert bits_equal(s.get_state(mmf.FIELD_W), Wo), name
+
+
+def test_bodies_run_to_tmax_then_continue(mmf, oracle, monkeypatch):
+    """A box with bodies through mmf_run (CUDA graph, the next step's eigenvalue from the tile estimates + wall cells):
+    run to a first tMax -- the trailing steps of the last batch switch themselves off and must keep the eigenvalue
+    candidate --, then continue on the same handle; every dt and the final state bitwise the oracle's."""
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
+    m = oracle.problem_mesh("radsod", 3, 32, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6], [6.2, 6.2, 6.2, 8.5, 7.5, 9.0]])
+    h = float(m["size"].min())
+    U = oracle.init_state(m)
+    Uo, Wo, Ro = U.copy(), np.zeros_like(U), np.zeros_like(U)
+    t, n = 0.0, 0
+    marks = []
+    for t_max in (0.05, 0.11):
+        while t < t_max:
+            dto, _ = oracle.step(m, 0.45, t, t_max, Uo, Wo, Ro)
+            t += dto
+            n += 1
+        marks.append((t, n))
+    with mmf.EulerSolver.from_mesh(m) as s:
+        assert s.info()["path"] == mmf.PATH_UNIFORM
+        s.set_state(mmf.FIELD_U, U)
+        t1, n1 = s.run(0.45, h, 0.0, 0.05)
+        assert (t1, n1) == marks[0]
+        t2, n2 = s.run(0.45, h, t1, 0.11)
+        assert (t2, n1 + n2) == marks[1]
+        assert bits_equal(s.get_state(mmf.FIELD_U), Uo)
 
 
 def test_unfused_operator_sequence_on_uniform_path(mmf, oracle):
@@ -283,7 +316,7 @@ def test_axis_order_flag_is_within_tolerance_not_exact(mmf, oracle):
 
 
 def test_mesh_with_bodies_path_selection(mmf, oracle, monkeypatch):
-    """A uniform box with bodies takes the fused path (kernel form 'c'); MMF_UNIFORM_BODIES=0 and MMF_FLAG_FORCE_GENERIC
+    """A uniform box with bodies takes the fused path (kernel form 'b'); MMF_UNIFORM_BODIES=0 and MMF_FLAG_FORCE_GENERIC
     keep it on the generic one."""
     boxes = np.array([[3.0, 3.0, 3.0, 5.0, 5.0, 5.0]])
     m = oracle.problem_mesh("radsod", 3, 16, boxes=boxes)

@@ -231,6 +231,7 @@ std::function<void()> bind_kernel(int form, const Args &a)
     case 'r': return [a] { uniform_stage_kernel_v5r<STAGE, ORDER, NW, false>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.xg); };
     case 't': return [a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, false>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW), in_desc(a, a.Un, NW - 2)); };
     case 'h': return [a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, true>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW + 1), in_desc(a, a.Un, NW - 1)); };
+    case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, true, true>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW + 1), in_desc(a, a.Un, NW - 1), a.solid); }) : nullptr;
     case 'c': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
     default: return nullptr;
     }
@@ -330,7 +331,7 @@ int emu_stage(int form, int stage, int order, int nw, int lz, const int dims[3],
     a.max_eig = max_eig;
     a.lz = lz;
     a.cta_est = cta_est;
-    const int rows = (form == 'h') ? nw - 1 : nw - 2; // rows a tile updates
+    const int rows = (form == 'h' || form == 'b') ? nw - 1 : nw - 2; // rows a tile updates
     const unsigned gx = (g.nx + XW - 1) / XW, gy = (g.ny + rows - 1) / rows, gz = (g.nz + lz - 1) / lz;
     a.hw = HaloWait{};
     a.hw.tx = (int) gx; a.hw.ty = (int) gy; a.hw.tz = (int) gz;

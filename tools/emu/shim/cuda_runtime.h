@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -125,6 +126,7 @@ inline double __longlong_as_double(long long v) { return emu::from_bits<double>(
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline int __double2hiint(double v) { return (int) (emu::to_bits(v) >> 32); }
+inline int __double2loint(double v) { return (int) (emu::to_bits(v) & 0xffffffffu); }
 inline double __hiloint2double(int hi, int lo) { return emu::from_bits<double>(((uint64_t) (unsigned) hi << 32) | (unsigned) lo); }
 
 inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v)
@@ -134,6 +136,14 @@ inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v)
     return old;
 }
 template <typename T> inline T atomicAdd(T *a, T v) { return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST); }
+inline double atomicAdd(double *a, double v)
+{
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    const double old = *a;
+    *a = old + v;
+    return old;
+}
 
 using std::min;
 using std::max;

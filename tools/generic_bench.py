@@ -61,7 +61,10 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--problem", default="vortex_xy")
-    ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain (the fused path then runs kernel form 'c')")
+    ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain (the fused path then runs kernel form 'b'; "
+                    "MMF_UNIFORM_BODIES=2: the rotate form 'c')")
+    ap.add_argument("--no-generic", action="store_true", help="time the fused path only")
+    ap.add_argument("--generic-only", action="store_true", help="time the generic path only")
     ap.add_argument("--dim", type=int, default=3, help="2: the 2-D vortex on size^2 cells (generic path only: the fused path is 3-D)")
     ap.add_argument("--two-level", type=int, default=0, metavar="N0", help="a 2:1 two-level octree of N0^3 coarse cells, every "
                     "other coarse cell refined (hanging faces; generic path only); random admissible state")
@@ -75,13 +78,15 @@ def main():
         return other_meshes(args)
     m = box_mesh(n, n, n, length / n, 0, origin=origin)
     if args.bodies:
-        os.environ.setdefault("MMF_UNIFORM_BODIES", "1")   # 1 = form b, 2 = form c
+        os.environ.setdefault("MMF_UNIFORM_BODIES", "1")   # 1 = kernel form 'b' (the default), 2 = the rotate form, 'c'
         lo = lambda f: [origin[e] + f[e] * length for e in range(3)]
         m = with_bodies(m, [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))])
     U = vortex_state(m)
     cells = m["volume"].shape[0]
     out = {}
     for name, flags in (("uniform", 0), ("generic", mmf.FLAG_FORCE_GENERIC)):
+        if (name == "generic" and args.no_generic) or (name == "uniform" and args.generic_only):
+            continue
         with mmf.EulerSolver.from_mesh(m, flags=flags) as s:
             path = s.info()["path"]
             s.set_state(mmf.FIELD_U, U)
@@ -90,11 +95,18 @@ def main():
             s.run(0.45, m["h"], 0.0, 1e30, max_steps=args.steps)
             ms = s.timer_stop()
             out[name] = s.get_state(mmf.FIELD_U)
-            print(json.dumps({"path": name, "path_code": path, "bodies_mode": os.environ.get("MMF_UNIFORM_BODIES", "") if args.bodies else "",
+            kernel_ms = None
+            if name == "uniform":   # per-launch times of the stage kernels (events around each launch: no graph, no overlap)
+                s.profile_begin()
+                s.run(0.45, m["h"], 0.0, 1e30, max_steps=args.steps)
+                kms, kn = s.profile_end()
+                kernel_ms = [kms[q] / max(kn[q], 1) for q in (1, 2, 3)]
+            print(json.dumps({"path": name, "stage_kernel_ms": kernel_ms, "path_code": path, "bodies_mode": os.environ.get("MMF_UNIFORM_BODIES", "") if args.bodies else "",
                               "generic_fused": os.environ.get("MMF_GENERIC_FUSED", "0"), "cells": cells, "solved_cells": int(m["solved"].sum()),
                               "ms_per_step": ms / args.steps,
                               "cell_updates_per_s": int(m["solved"].sum()) * 3 * args.steps / (ms * 1e-3)}), flush=True)
-    print(json.dumps({"bitwise_equal": bool(np.array_equal(out["uniform"], out["generic"]))}))
+    if "generic" in out and "uniform" in out:
+        print(json.dumps({"bitwise_equal": bool(np.array_equal(out["uniform"], out["generic"]))}))
 
 
 if __name__ == "__main__":
