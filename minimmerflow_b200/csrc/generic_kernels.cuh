@@ -169,36 +169,6 @@ __device__ __forceinline__ void bc_values_of_derived(int bc, const double *norma
     }
 }
 
-// What a thread needs of one entry of its cell's list before any arithmetic: the interface's record and -- for an
-// interior interface -- the state of the cell on the other side.  Three dependent loads (entry -> interface record ->
-// other cell -> its five values); generic_cell_residual fetches the NEXT entry's while it works on the current one
-// (MMF_GEN_PREFETCH = 1; measured before it becomes the default: the serial walk entry by entry was bound by exactly this chain,
-// profiles/r02h_generic.md).
-#ifndef MMF_GEN_PREFETCH
-#define MMF_GEN_PREFETCH 0
-#endif
-// (MMF_GEN_PREFETCH=2: only the interface record and the other cell's id are fetched ahead -- ten registers fewer --,
-//  its five values when the entry's turn comes)
-struct EntryFetch {
-    int side, bc;
-    int32_t other; // the cell on the other side (interior interfaces only)
-    double A, nrm[3];
-    double oc[NF]; // ... and its conservative state
-};
-
-__device__ __forceinline__ void fetch_entry(const GenericMesh &m, const double *__restrict__ S, const int64_t e, EntryFetch &r)
-{
-    const int32_t ent = m.cf_ent[e];
-    const int32_t f   = ent >> 1;
-    r.side = ent & 1;
-    r.bc   = m.f_bc[f];
-    r.A    = m.f_area[f];
-    r.nrm[0] = m.f_normal[f]; r.nrm[1] = m.f_normal[m.n_ifaces + f]; r.nrm[2] = m.f_normal[2 * m.n_ifaces + f];
-    r.other = (r.bc == BC_NONE) ? (r.side == 0 ? m.f_neigh[f] : m.f_owner[f]) : 0;
-    // order-1 reconstruction: face state = cell mean (src/reconstruction.cpp:90-97)
-    if (MMF_GEN_PREFETCH != 2 && r.bc == BC_NONE) load_cell(S, m.stride, r.other, r.oc);
-}
-
 // One cell's residual: its interfaces in the reference's processing order, `-=` on the owner side and `+=` on
 // the neighbour side (src/euler.cpp:150-247); lmax = running maximum of the interface eigenvalues (:234).
 // Only solved cells have a list, so on a boundary / wall interface the gathering cell is the fluid side
@@ -208,30 +178,22 @@ __device__ __forceinline__ void generic_cell_residual(const GenericMesh &m, cons
 {
     const int64_t e0 = m.cf_ptr[c], e1 = m.cf_ptr[c + 1];
     if (e0 == e1) return;
-    EntryFetch nxt;
-    if (MMF_GEN_PREFETCH) fetch_entry(m, S, e0, nxt);
     const GenericDivConsts dk = generic_div_consts();
     DerivedCell own;
     load_cell(S, m.stride, c, own.cons);
     derive_cell_generic(own, dk);
-#pragma unroll 1
     for (int64_t e = e0; e < e1; ++e) {
-        EntryFetch cur;
-        if (MMF_GEN_PREFETCH) {
-            cur = nxt;
-            if (e + 1 < e1) fetch_entry(m, S, e + 1, nxt);
-        } else {
-            fetch_entry(m, S, e, cur);
-        }
-        const int side = cur.side, bc = cur.bc;
-        const double A = cur.A;
-        const double nrm[3] = { cur.nrm[0], cur.nrm[1], cur.nrm[2] };
+        const int32_t ent  = m.cf_ent[e];
+        const int32_t f    = ent >> 1;
+        const int     side = ent & 1;
+        const int     bc   = m.f_bc[f];
+        const double  A    = m.f_area[f];
+        const double  nrm[3] = { m.f_normal[f], m.f_normal[m.n_ifaces + f], m.f_normal[2 * m.n_ifaces + f] };
 
         DerivedCell other;
         if (bc == BC_NONE) {
-            if (MMF_GEN_PREFETCH == 2) load_cell(S, m.stride, cur.other, cur.oc);
-#pragma unroll
-            for (int k = 0; k < NF; ++k) other.cons[k] = cur.oc[k];
+            // order-1 reconstruction: face state = cell mean (src/reconstruction.cpp:90-97)
+            load_cell(S, m.stride, side == 0 ? m.f_neigh[f] : m.f_owner[f], other.cons);
         } else if (side == 0) {
             bc_values_of_derived(bc, nrm, m.dirichlet_info, own, other.cons);
         } else {

@@ -65,12 +65,6 @@ __host__ __device__ constexpr int t_unroll(int nw) { return MMF_T_UNROLL > 0 ? M
 #define MMF_T_EARLY_RELEASE 1
 #endif
 
-// the NEXT plane's cell is read and derived (primitives, sound speed: one long dependency chain) inside the step of
-// the current plane, whose interface fluxes have the independent work to hide it behind
-#ifndef MMF_T_PIPE
-#define MMF_T_PIPE 0
-#endif
-
 // Rows of a CTA's tile.  Two halo warps (MH = false): warps 0 and NW-1 serve the low and the high halo row, NW-2 warps
 // update.  Merged halo warp (MH = true): warp 0 serves BOTH halo rows -- it publishes the record of the row below the
 // tile and turns the record of the tile's top row into that row's -y_hi; together that is 175 FP64 instructions per
@@ -305,14 +299,6 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
 #pragma unroll
             for (int k = 0; k < NF; ++k) pUc[k] = c0[k];
         }
-        double nU[NF]; // (MMF_T_PIPE) the next plane's cell and its derived state
-        CellPrim nq;
-        if (MMF_T_PIPE) {
-            mbar_wait(&full[1 % D], (unsigned) ((1 / D) & 1));
-#pragma unroll
-            for (int k = 0; k < NF; ++k) nU[k] = ring[(1 % D) * SLOT + k * FSTR + own];
-            derive_cell(nU, dc, nq);
-        }
 
 #pragma unroll UNROLL
         for (int s = 1; s <= nsteps; ++s) {
@@ -320,26 +306,15 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             const unsigned par = (unsigned) ((s - 1) & 1);
             const double *ts = ring + (s % D) * SLOT;       // this plane
             const double *tp = ring + ((s - 1) % D) * SLOT; // the previous plane
+            mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
             double cU[NF];
-            CellPrim q;
-            if (MMF_T_PIPE) {
-                // plane s was read and derived during step s-1; now plane s+1 (it exists: the ring runs to step nsteps+1)
-                mbar_wait(&full[(s + 1) % D], (unsigned) (((s + 1) / D) & 1));
 #pragma unroll
-                for (int k = 0; k < NF; ++k) cU[k] = nU[k];
-                q = nq;
-#pragma unroll
-                for (int k = 0; k < NF; ++k) nU[k] = ring[((s + 1) % D) * SLOT + k * FSTR + own];
-                derive_cell(nU, dc, nq);
-            } else {
-                mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
-#pragma unroll
-                for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own];
-            }
+            for (int k = 0; k < NF; ++k) cU[k] = ts[k * FSTR + own];
             const unsigned csol = nsol;
             if (BODY) { moff += mplane; nsol = solid[moff]; } // plane z0+s: at most the ghost plane nz
 
-            if (!MMF_T_PIPE) derive_cell(cU, dc, q);
+            CellPrim q;
+            derive_cell(cU, dc, q);
 
             // ---- y record for row+1 (the earlier it is out, the less row+1 waits) ---------------------
             double cFy[NF], cly;
@@ -478,12 +453,12 @@ uniform_stage_kernel_t(const UniformGeom g, double *Out, const StepControl *__re
             const int s = nsteps + 1;
             const double *ts = ring + (s % D) * SLOT;
             const double *tp = ring + ((s - 1) % D) * SLOT;
-            if (!MMF_T_PIPE) mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
+            mbar_wait(&full[s % D], (unsigned) ((s / D) & 1));
             double cU[NF], pU[NF], pUn[NF];
 #pragma unroll
-            for (int k = 0; k < NF; ++k) { cU[k] = MMF_T_PIPE ? nU[k] : ts[k * FSTR + own]; pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own]; }
+            for (int k = 0; k < NF; ++k) { cU[k] = ts[k * FSTR + own]; pU[k] = CARRY ? pUc[k] : tp[k * FSTR + own]; }
             CellPrim q;
-            if (MMF_T_PIPE) q = nq; else derive_cell(cU, dc, q);
+            derive_cell(cU, dc, q);
             double cFz[NF], clz, AFz[NF];
             axis_flux<2>(q, cFz, clz);
             if (BODY) clz = body_mark(clz, nsol);
