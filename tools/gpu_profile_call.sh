@@ -15,8 +15,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit code: $?"; tail -c 2000 gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-bodies > gpurun_out/${TAG}_launches.log 2>&1
 echo "launch list exit code: $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:uniform_stage_kernel -s 9 -c 3 -f -o gpurun_out/${TAG}_stage \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-bodies > gpurun_out/${TAG}_ncu.log 2>&1
 echo "ncu --set full exit code: $?"; ls -la gpurun_out/ | grep "$TAG"

@@ -101,15 +101,18 @@ def main():
         text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
         chunks = re.split(r"\n(?=\s*Function : )", text)
         # (ELb0 = padded x ghost columns: the single-GPU instantiation the bench runs)
-        want = {"uniform_stage_kernel_tILi0ELi0ELi12ELi4ELb1E": "stage0_rhs_only_h_12warps",
-                "uniform_stage_kernel_tILi1ELi0ELi12ELi4ELb1E": "stage1_h_12warps",
-                "uniform_stage_kernel_tILi2ELi0ELi12ELi4ELb1E": "stage2_h_12warps",
-                "uniform_stage_kernel_tILi3ELi0ELi12ELi4ELb1E": "stage3_h_12warps",
-                "uniform_stage_kernel_tILi2ELi0ELi16ELi4ELb0E": "stage2_t_16warps",
+        want = {"uniform_stage_kernel_tILi0ELi0ELi12ELi4ELb1ELb0E": "stage0_rhs_only_h_12warps",
+                "uniform_stage_kernel_tILi1ELi0ELi12ELi4ELb1ELb0E": "stage1_h_12warps",
+                "uniform_stage_kernel_tILi2ELi0ELi12ELi4ELb1ELb0E": "stage2_h_12warps",
+                "uniform_stage_kernel_tILi3ELi0ELi12ELi4ELb1ELb0E": "stage3_h_12warps",
+                "uniform_stage_kernel_tILi2ELi0ELi16ELi4ELb0ELb0E": "stage2_t_16warps",
+                # a box with bodies (kernel form 'b'): the same kernel with the flag array
+                "uniform_stage_kernel_tILi2ELi0ELi12ELi4ELb1ELb1E": "stage2_b_bodies_12warps",
+                "uniform_eig_wall_kernel": "uniform_eig_wall",
                 # the rotate form (per-thread global loads): what runs when an x side is a partition side
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb0": "stage2_v5r_12warps",
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb1": "stage2_v5r_12warps_xghost",
-                # a box with bodies: the rotate form that skips flagged cells, and the pass over the wall cells
+                # ... and the rotate form for it (MMF_UNIFORM_BODIES=2), the pass over the wall cells
                 "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb1": "stage2_v5rb_bodies_12warps",
                 "uniform_wall_cells_kernelILi2ELi0": "stage2_wall_cells",
                 "uniform_eig_body_kernel": "uniform_eig_body",
