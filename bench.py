@@ -487,10 +487,18 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = float(np.median(repeats_ms))
 
-    # per-kernel device time of the fused stage kernels, CUDA events on the launching stream
-    s.profile_begin()
-    s.run(cfl, h, 0.0, t_inf, max_steps=args.steps)
-    kms, kn = s.profile_end()
+    # per-kernel device time of the fused stage kernels, CUDA events on the launching stream around every launch.  With
+    # several ranks a boundary CTA waits IN the kernel for its neighbours' layers, so a launch also measures how far the
+    # ranks drifted apart at that moment: the leg runs as five segments between barriers and reports the per-stage MEDIAN
+    # of the segments' averages (at 8 GPUs a single late neighbour once put 27 ms into one stage-2 launch)
+    seg_steps = max(args.steps // 5, 2)
+    seg_ms = []
+    for _ in range(5):
+        barrier()
+        s.profile_begin()
+        s.run(cfl, h, 0.0, t_inf, max_steps=seg_steps)
+        kms, kn = s.profile_end()
+        seg_ms.append([kms[i] / kn[i] if kn[i] else None for i in (1, 2, 3)])
 
     # e2e: the call sequence a host like main.cpp makes, with HOST buffers and wall-clock time:
     # upload the AoS state (pinned), K x mmf_step -- each returns dt and the three max eigenvalues
@@ -546,11 +554,12 @@ def run_ours(args):
     if rank == 0:
         value = cells_total * 3.0 * args.steps / (ms * 1e-3)
         peak, peak_src = measured_peak()
-        stage_ms = [kms[i] / kn[i] if kn[i] else None for i in (1, 2, 3)]
+        stage_ms = [float(np.median([seg[i] for seg in seg_ms])) if all(seg[i] is not None for seg in seg_ms) else None
+                    for i in range(3)]
         stage_gbs = [ALG_BYTES_PER_CELL_STAGE[i] * cells_local / (stage_ms[i] * 1e-3) / 1e9 if stage_ms[i] else None
                      for i in range(3)]
         # dominant kernel: the stage-2/3 kernel (one template, two of the three launches of a step)
-        dom_ms = (kms[2] + kms[3]) / max(kn[2] + kn[3], 1)
+        dom_ms = 0.5 * (stage_ms[1] + stage_ms[2]) if stage_ms[1] and stage_ms[2] else None
         achieved = ALG_BYTES_PER_CELL_STAGE[1] * cells_local / (dom_ms * 1e-3) / 1e9 if dom_ms else None
         step_gbs = sum(ALG_BYTES_PER_CELL_STAGE) * cells_local / (ms / args.steps * 1e-3) / 1e9
         # DRAM bytes of one launch of the dominant kernel: from the round's own `ncu --set full` capture of this
@@ -598,6 +607,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL_STAGE[1] * cells_local,
                          "avg_launch_ms": dom_ms,
                          "stage_ms": stage_ms, "stage_GBps": stage_gbs,
+                         "stage_ms_how": f"CUDA events around every launch of the stage kernels, 5 segments of {seg_steps} steps "
+                                         f"between barriers, per-stage median of the segments' averages",
                          "algorithmic_bytes_per_cell": list(ALG_BYTES_PER_CELL_STAGE),
                          "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                         "what": "320 B/cell per RK3 step over the timed step time (all kernels, launch gaps included)"}},
