@@ -244,7 +244,7 @@ static int comm_set_box_neighbours(mmf_ctx *ctx, const int32_t ranks[6])
     if (ctx->path != MMF_PATH_UNIFORM) return fail(ctx, MMF_ERR_STATE, "box neighbours apply to the uniform path");
     UniformPath *u = ctx->uni;
     const UniformGeom &g = u->g;
-    if (u->bodies) { // kernel form 'c' has no halo wait and no tile order: a box with bodies is a single-GPU box
+    if (u->bodies) { // the wall-cell passes know no partition sides: a box with bodies is a single-GPU box
         return fail(ctx, MMF_ERR_INVALID, "a uniform box with bodies cannot be partitioned: describe the ranks' meshes "
                     "for the generic path (MMF_FLAG_FORCE_GENERIC or MMF_UNIFORM_BODIES=0)");
     }

@@ -1,10 +1,10 @@
 // stage_tu.cu -- one translation unit per (kernel form, stage): the Makefile compiles this file with
-// -DMMF_TU_FORM=<r|c|t> -DMMF_TU_FORM_ID=<0|1|2> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
+// -DMMF_TU_FORM=<r|t> -DMMF_TU_FORM_ID=<0|2> -DMMF_TU_STAGE=<0..3>, so that the stage-kernel instantiations
 // (3 accumulation orders x CTA shapes x padded / compact x ghosts per form and stage) build in parallel.
 //   r = the rotate form (uniform_stage_v5r.cuh), the default of every stage
-//   c = the rotate form for a box with bodies (uniform_stage_v5rb.cuh), wall cells by a small pass around it
 //   t = the same scheme with its input staged in shared memory by bulk tensor (TMA) loads (uniform_stage_t.cuh);
-//       also serves form 'h' (one warp for both halo rows) and form 'b' (form 'h' for a box with bodies)
+//       also serves form 'h' (one warp for both halo rows) and form 'b' (form 'h' for a box with bodies, the wall
+//       cells by a small pass around it: uniform_body_cells.cuh)
 #include "uniform_launch.cuh"
 
 #ifndef MMF_TU_FORM_ID // a bare `nvcc -c stage_tu.cu` (no Makefile): the rotate form, RHS only
@@ -15,19 +15,18 @@
 
 #if MMF_TU_FORM_ID == 0
 #include "uniform_stage_v5r.cuh"
-#elif MMF_TU_FORM_ID == 1
-#include "uniform_stage_v5rb.cuh"
 #elif MMF_TU_FORM_ID == 2
-#include "uniform_stage_v5rb.cuh" // (the wall-cell kernels around form 'b')
+#include "uniform_stage_v5r.cuh"
+#include "uniform_body_cells.cuh"
 #include "uniform_stage_t.cuh"
 #else
-#error "MMF_TU_FORM_ID must be 0 (r), 1 (c) or 2 (t)"
+#error "MMF_TU_FORM_ID must be 0 (r) or 2 (t)"
 #endif
 
 namespace mmf {
 
-#if MMF_TU_FORM_ID == 1 || MMF_TU_FORM_ID == 2
-// a box with bodies (forms 'b' and 'c'): the wall cells' results into the compact buffer BEFORE the stage kernel runs
+#if MMF_TU_FORM_ID == 2
+// a box with bodies (form 'b'): the wall cells' results into the compact buffer BEFORE the stage kernel runs
 // (it does not store them, and stage 3 updates U in place), and from the buffer into the output array behind it
 template <int STAGE, int ORDER>
 static int launch_wall_cells(mmf_ctx *ctx, const double *Sin, const double *Un, double *d_max)
@@ -60,12 +59,7 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
 {
     UniformPath *u = ctx->uni;
     const StageShape sh = u->shape[STAGE];
-#if MMF_TU_FORM_ID == 1
-    (void) sh;
-    if (int rc = launch_wall_cells<STAGE, ORDER>(ctx, Sin, Un, d_max)) return rc;
-    if (int rc = launch_stage_body(ctx, uniform_stage_kernel_v5rb<STAGE, ORDER, 12, true>, STAGE, Sin, Un, Out, d_max)) return rc;
-    return launch_wall_scatter<STAGE>(ctx, Out);
-#elif MMF_TU_FORM_ID == 2
+#if MMF_TU_FORM_ID == 2
     // (compact x ghost columns -- an x partition side -- are only read by the rotate form: comm_ipc_import switches the
     //  stages' shapes to it)
     if (uniform_use_xghost(ctx)) return fail(ctx, MMF_ERR_STATE, "stage-kernel forms 't' / 'h' cannot read compact x ghost columns");
@@ -75,7 +69,7 @@ static int launch_stage_o(mmf_ctx *ctx, const double *Sin, const double *Un, dou
                                      stage_t_smem_bytes(12, STAGE, T_DEPTH, true), Sin, Un, Out, d_max, u->solid)) return rc;
         return launch_wall_scatter<STAGE>(ctx, Out);
     }
-    if (u->bodies) return fail(ctx, MMF_ERR_STATE, "a box with bodies runs kernel form 'b' or 'c'");
+    if (u->bodies) return fail(ctx, MMF_ERR_STATE, "a box with bodies runs kernel form 'b'");
 #define MMF_LAUNCH_T(NWV, DV, MHV) return launch_stage_tl(ctx, uniform_stage_kernel_t<STAGE, ORDER, NWV, DV, MHV>, STAGE, NWV, MHV, stage_t_smem_bytes(NWV, STAGE, DV, MHV), Sin, Un, Out, d_max)
     if (sh.form == 'h') { if (sh.nw == 12) MMF_LAUNCH_T(12, T_DEPTH, true); MMF_LAUNCH_T(16, T_DEPTH, true); }
     if (sh.nw == 16) MMF_LAUNCH_T(16, T_DEPTH, false);

@@ -184,7 +184,7 @@ __device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const doub
                                                 const unsigned char *__restrict__ solid, const int i, const int j, const int k)
 {
     const long long o = uoff(g, i, j, k);
-    if (solid[o] == 1) return 0.0; // (2 = a fluid cell next to a wall, kernel form 'c')
+    if (solid[o] == 1) return 0.0; // (2 = a fluid cell next to a wall)
     DivConsts dc;
     dc.y_gm1 = rcp_nr(GM1); dc.y_c1 = rcp_nr(TWO_OVER_GM1); dc.y_vol = 0.0;
     double c[NF];
@@ -222,7 +222,7 @@ __device__ __forceinline__ double eig_body_cell(const UniformGeom &g, const doub
     return lmax;
 }
 
-// ---- a box with bodies, fix-up formulation (kernel form 'c') ------------------------------------------------
+// ---- a box with bodies, fix-up formulation (kernel form 'b') ------------------------------------------------
 // Flag values: 0 = fluid, 1 = not solved (solid), 2 = fluid cell with at least one wall interface.  The stage
 // kernel proper treats a wall like an ordinary interface (its result for a flag-2 cell is meaningless and is
 // not stored); those cells -- a surface -- are recomputed here, one thread per cell, reference-shaped: the
@@ -326,7 +326,7 @@ __device__ __forceinline__ double wall_cell_update(const UniformGeom &g, const L
 // ---- a box with bodies: the flag array and the wall-cell list, host side --------------------------------------
 // One flag per padded cell (layout of one field): 1 = not solved (src/main.cpp:221-237).  The ghost shell repeats
 // the flag of the cell it touches, so that the border interface of an unsolved cell is skipped like the
-// reference skips it (src/euler.cpp:181-183).  mark_walls (kernel form 'c'): fluid cells with at least one wall
+// reference skips it (src/euler.cpp:181-183).  mark_walls (kernel form 'b'): fluid cells with at least one wall
 // interface get flag 2 and are listed by padded offset, ascending; their ghost cells keep 0.
 // Plain host code (no CUDA calls), shared with tools/emu so that it is unit-tested on the CPU.
 inline void body_flags(const UniformGeom &g, const long long n_cells, const int *cell_ijk, const unsigned char *solved,

@@ -19,7 +19,6 @@ namespace mmf {
 //   'h' form 't' with ONE warp serving both halo rows of the tile: nw - 1 update rows per CTA
 //   'b' form 'h' for a box WITH BODIES (12 warps; chosen by the path itself, never by MMF_STAGE_CFG): one flag byte per
 //       cell, the wall cells recomputed by a small pass around the stage kernel
-//   'c' the rotate form for a box with bodies (uniform_stage_v5rb.cuh, 12 warps; MMF_UNIFORM_BODIES=2), likewise
 struct StageShape {
     char form = 'r';
     int nw = 12;
@@ -52,7 +51,7 @@ struct UniformPath {
     // which the stage kernel does not store and wall_cell_update recomputes (list of their padded offsets, compact
     // result buffer); the ghost shell repeats the flag of the cell it touches
     unsigned char *solid = nullptr;
-    bool bodies = false;              // set before the arrays are laid out: selects kernel form 'c' for every stage
+    bool bodies = false;              // set before the arrays are laid out: selects kernel form 'b' for every stage
     int *wall_list = nullptr;
     int n_wall = 0;
     double *wall_compact = nullptr;
@@ -265,28 +264,6 @@ static int launch_stage_tl(mmf_ctx *ctx, K kern, int stage, int nw, bool merged_
     return MMF_OK;
 }
 
-// form 'c' (a box with bodies, single GPU): the 12-warp rotate-form geometry plus the flag array
-template <typename K>
-static int launch_stage_body(mmf_ctx *ctx, K kern, int stage, const double *Sin, const double *Un, double *Out, double *d_max)
-{
-    UniformPath *u = ctx->uni;
-    const UniformGeom &g = u->g;
-    const int nw = 12, lz = u->shape[stage].lz, rows = u->shape[stage].rows();
-    if (!u->solid) return fail(ctx, MMF_ERR_INVALID, "stage-kernel form 'c' needs the flag array of a box with bodies");
-    dim3 grid((g.nx + XW - 1) / XW, (g.ny + rows - 1) / rows, (g.nz + lz - 1) / lz);
-    const size_t smem = (size_t) nw * 16 * 32 * sizeof(double) + 2 * nw * sizeof(unsigned long long);
-    MMF_CUDA(ctx, stage_smem_attribute(kern, smem));
-    HaloWait hw{};
-    hw.tx = (int) grid.x; hw.ty = (int) grid.y; hw.tz = (int) grid.z;
-    {
-        ScopedLaunchTimer timer(ctx, stage);
-        kern<<<grid, nw * 32, smem, ctx->stream>>>(g, Sin, Un, Out, ctx->d_ctl, d_max, lz, (stage == 3) ? u->cta_est : nullptr,
-                                                   uniform_load_clamp(u), hw, u->solid);
-    }
-    MMF_LAUNCH_CHECK(ctx);
-    return MMF_OK;
-}
-
 // ---- per (form, stage) launchers, defined in stage_tu.cu ----------------------------------------------
 // order = NUM_MORTON / NUM_LEXI / NUM_AXIS; CTA shape and z chunk come from ctx->uni->shape[stage]
 typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const double *Un, double *Out, double *d_max);
@@ -299,19 +276,17 @@ typedef int (*StageLauncher)(mmf_ctx *ctx, int order, const double *Sin, const d
     int MMF_STAGE_TU_NAME(F, 2)(mmf_ctx *, int, const double *, const double *, double *, double *);   \
     int MMF_STAGE_TU_NAME(F, 3)(mmf_ctx *, int, const double *, const double *, double *, double *);
 MMF_DECLARE_STAGE_TUS(r)  // uniform_stage_v5r.cuh
-MMF_DECLARE_STAGE_TUS(c)  // uniform_stage_v5rb.cuh, a box with bodies
 MMF_DECLARE_STAGE_TUS(t)  // uniform_stage_t.cuh: input staged by bulk tensor loads
 #undef MMF_DECLARE_STAGE_TUS
 
-// the launcher of a kernel form ('r', 'c', 't' / 'h' / 'b') for a stage
+// the launcher of a kernel form ('r', 't' / 'h' / 'b') for a stage
 inline StageLauncher stage_launcher(char form, int stage)
 {
-    static const StageLauncher tab[3][4] = {
+    static const StageLauncher tab[2][4] = {
         { launch_stage_r_0, launch_stage_r_1, launch_stage_r_2, launch_stage_r_3 },
-        { launch_stage_c_0, launch_stage_c_1, launch_stage_c_2, launch_stage_c_3 },
         { launch_stage_t_0, launch_stage_t_1, launch_stage_t_2, launch_stage_t_3 },
     };
-    return tab[(form == 'c') ? 1 : (form == 't' || form == 'h' || form == 'b') ? 2 : 0][stage];
+    return tab[(form == 't' || form == 'h' || form == 'b') ? 1 : 0][stage];
 }
 
 } // namespace mmf

@@ -183,10 +183,9 @@ static int uniform_alloc(mmf_ctx *ctx, UniformPath *u)
         }
     }
     if (u->bodies) {
-        // a box with bodies: the kernel forms that know about them, whatever MMF_STAGE_CFG says -- 'b', the TMA-fed kernel
-        // with one warp for both halo rows plus the flag array; MMF_UNIFORM_BODIES=2: 'c', the rotate form plus the flag
-        const bool rotate = getenv("MMF_UNIFORM_BODIES") && atoi(getenv("MMF_UNIFORM_BODIES")) == 2;
-        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ rotate ? 'c' : 'b', 12 };
+        // a box with bodies: the kernel form that knows about them, whatever MMF_STAGE_CFG says -- 'b', the TMA-fed kernel
+        // with one warp for both halo rows plus the flag array
+        for (int st = 0; st < 4; ++st) u->shape[st] = StageShape{ 'b', 12 };
     }
     u->clamp_ff = true;
     u->halo_inkernel = u->clamp_ff && !(getenv("MMF_HALO_WAIT_KERNEL") && atoi(getenv("MMF_HALO_WAIT_KERNEL")));

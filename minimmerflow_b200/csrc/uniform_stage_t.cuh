@@ -22,7 +22,7 @@
 //
 // Not here: compact x ghost columns (XGhost: partition sides across x).  Such launches keep the rotate form.
 //
-// BODY = true (kernel form 'b'): the same kernel for a uniform box WITH BODIES, by the scheme uniform_stage_v5rb.cuh
+// BODY = true (kernel form 'b'): the same kernel for a uniform box WITH BODIES, by the scheme uniform_body_cells.cuh
 // explains -- one flag byte per padded cell (1 = not solved, 2 = fluid cell with a wall interface); a cell that is not
 // solved reports a NEGATIVE max eigenvalue in its x / y / z record (the sign bit is set: a negative value never raises a
 // maximum, and max(lam_fluid, negative) = lam_fluid is in the true maximum anyway), a wall is evaluated like any

@@ -1,5 +1,5 @@
 // uniform_stage_v5.cuh -- fused residual + RK-stage kernels ("low-face streaming"): the scheme and the pieces every
-// form shares (the kernels themselves: uniform_stage_v5r.cuh, and uniform_stage_v5rb.cuh for a box with bodies).
+// form shares (the kernels themselves: uniform_stage_v5r.cuh and uniform_stage_t.cuh; uniform_body_cells.cuh for a box with bodies).
 //
 // Tiling (uniform_kernels.cuh): a warp owns a 32-cell x window (30 updated, +-x data by warp shuffle), the
 // CTA's NW warps are consecutive y rows (rows 0 and NW-1 are halo rows), the CTA marches along z with plane

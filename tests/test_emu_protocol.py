@@ -96,11 +96,11 @@ def test_compact_x_ghost_columns_on_the_emulator(emu, oracle, form):
     assert np.array_equal(box.gather(R), ref)
 
 
-@pytest.mark.parametrize("form", ["c", "b"])
+@pytest.mark.parametrize("form", ["b"])
 @pytest.mark.parametrize("chaos", [0, 300])
 def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, chaos, form):
-    """Kernel forms 'c' (uniform_stage_v5rb.cuh) and 'b' (uniform_stage_t.cuh with BODY: the TMA-fed kernel; the
-    default), wall cells recomputed by wall_cell_update around a stage kernel without a slow path: a uniform box
+    """Kernel form 'b' (uniform_stage_t.cuh with BODY: the TMA-fed kernel plus one flag byte per cell), wall cells
+    recomputed by wall_cell_update (uniform_body_cells.cuh) around a stage kernel without a slow path: a uniform box
     with bodies -- unsolved cells, wall interfaces
     evaluated against the fluid cell's mirror image, solid | solid interfaces skipped -- and the eigenvalue
     pass that chooses dt there (eig_body_cell), bit for bit against the oracle."""
@@ -118,13 +118,13 @@ def test_body_stage_kernel_source_matches_oracle_on_the_emulator(emu, oracle, ch
     # reflecting borders with a body on them
     m = with_bodies(lexicographic_box_mesh(7, 23, 4, 0.5, 1), [[-1, 4.1, -1, 1.4, 6.4, 9.0], [2.1, 10.1, 0.6, 2.9, 11.4, 1.4]])
     m["problem"] = "radsod"
-    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, form, 8 if form == "c" else 12, 3, 2, chaos, 3)
+    assert run_emu.check_case(emu, oracle, "box 7x23x4 + bodies", dict(m), 1, form, 12, 3, 2, chaos, 3)
 
 
 BODY_CASES_3D = [c for c in reference_cases() if c["dim"] == 3 and c.get("bodies")]
 
 
-@pytest.mark.parametrize("form", ["c", "b"])
+@pytest.mark.parametrize("form", ["b"])
 @pytest.mark.parametrize("case", BODY_CASES_3D, ids=lambda c: c["name"])
 def test_body_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu, oracle, case, form):
     """The whole run of a reference case with bodies -- dt from the eigenvalue pass (eig_body_cell), three fused
@@ -200,7 +200,7 @@ def test_stage_kernel_source_reproduces_the_reference_fields_on_the_emulator(emu
 
 def test_host_side_body_flags_and_wall_list(emu, oracle):
     """body_flags (uniform_device.cuh), the host code uniform_try_create runs for a box with bodies: flag array
-    with the replicated ghost shell and -- kernel form 'c' -- flag 2 plus the ascending list of fluid cells that
+    with the replicated ghost shell and -- kernel form 'b' -- flag 2 plus the ascending list of fluid cells that
     touch a wall, against the independent construction of the test harness (run_emu.Box)."""
     import ctypes as C
     I = C.POINTER(C.c_int)

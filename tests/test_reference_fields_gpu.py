@@ -20,7 +20,7 @@ def test_resident_run_matches_reference_fields(mmf, oracle, case):
     n = case["name"]
     m = case_mesh(oracle, case)
     with mmf.EulerSolver.from_mesh(m, dirichlet_info=dirichlet_info(case)) as s:
-        # every 3-D box takes the fused path, with bodies (kernel form 'c') or without, unless MMF_UNIFORM_BODIES=0
+        # every 3-D box takes the fused path, with bodies (kernel form 'b') or without, unless MMF_UNIFORM_BODIES=0
         bodies_fused = os.environ.get("MMF_UNIFORM_BODIES", "1") not in ("", "0")
         fused = m["dim"] == 3 and (bodies_fused or not case.get("bodies"))
         assert s.info()["path"] == (mmf.PATH_UNIFORM if fused else mmf.PATH_GENERIC)

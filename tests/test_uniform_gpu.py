@@ -123,17 +123,12 @@ def _body_meshes(oracle):
     yield "box 37x29x11 + bodies", m
 
 
-@pytest.mark.parametrize("form", ["b", "c"])
-def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch, form):
-    """Kernel forms 'b' (the default: the TMA-fed kernel with the flag array, uniform_stage_t.cuh BODY) and 'c'
-    (MMF_UNIFORM_BODIES=2: the rotate form with it, uniform_stage_v5rb.cuh), both + wall_cell_update: a uniform box with
-    bodies takes the fused path by itself -- RHS, the dt eigenvalue (full pass at the first step, then from the stage-3
+def test_uniform_path_with_bodies_bit_exact(mmf, oracle, monkeypatch):
+    """Kernel form 'b' (the TMA-fed kernel with the flag array, uniform_stage_t.cuh BODY) + wall_cell_update: a uniform
+    box with bodies takes the fused path by itself -- RHS, the dt eigenvalue (full pass at the first step, then from the stage-3
     tile estimates, the wall cells and the border ghosts), ten fused steps and the unfused operator sequence, bitwise
     against the oracle; cells that are not solved keep the host's values."""
-    if form == "b":
-        monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
-    else:
-        monkeypatch.setenv("MMF_UNIFORM_BODIES", "2")
+    monkeypatch.delenv("MMF_UNIFORM_BODIES", raising=False)
     rng = np.random.default_rng(11)
     for name, m in _body_meshes(oracle):
         nc = m["volume"].shape[0]

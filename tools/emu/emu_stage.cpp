@@ -178,7 +178,7 @@ alignas(128) double smem[40 * 1024]; // the kernels' `extern __shared__ double s
 }
 
 #include "uniform_stage_v5r.cuh"
-#include "uniform_stage_v5rb.cuh"
+#include "uniform_body_cells.cuh"
 #include "uniform_stage_t.cuh"
 #include "uniform_eligibility.h"
 #include "generic_kernels.cuh"
@@ -199,7 +199,7 @@ struct Args {
     LoadClamp lc;
     HaloWait hw;
     XGhost xg;
-    const unsigned char *solid; // form 'c': flag array of a box with bodies
+    const unsigned char *solid; // form 'b': flag array of a box with bodies
 };
 
 // the emulated descriptor of a padded state array for the bulk tensor loads of form 't' (uniform_in_map)
@@ -232,7 +232,6 @@ std::function<void()> bind_kernel(int form, const Args &a)
     case 't': return [a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, false>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW), in_desc(a, a.Un, NW - 2)); };
     case 'h': return [a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, true>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW + 1), in_desc(a, a.Un, NW - 1)); };
     case 'b': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_t<STAGE, ORDER, NW, T_DEPTH, true, true>(a.g, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, in_desc(a, a.Sin, NW + 1), in_desc(a, a.Un, NW - 1), a.solid); }) : nullptr;
-    case 'c': return a.solid ? std::function<void()>([a] { uniform_stage_kernel_v5rb<STAGE, ORDER, NW, true>(a.g, a.Sin, a.Un, a.Out, a.ctl, a.max_eig, a.lz, a.cta_est, a.lc, a.hw, a.solid); }) : nullptr;
     default: return nullptr;
     }
 }
@@ -291,7 +290,7 @@ void emu_set_xghost(const double *lo, const double *hi, long long fs, int pitch)
     g_xghost.lo = lo; g_xghost.hi = hi; g_xghost.fs = fs; g_xghost.pitch = pitch;
 }
 
-// flag array (padded layout of one field, 1 = not solved, 2 = wall cell) for the NEXT emu_stage calls of form 'c'
+// flag array (padded layout of one field, 1 = not solved, 2 = wall cell) for the NEXT emu_stage calls of form 'b'
 void emu_set_solid(const unsigned char *solid) { g_solid = solid; }
 
 // padded extents of a box, as uniform_alloc (uniform_path.cuh) lays them out
@@ -373,7 +372,7 @@ double emu_eig_body(const int dims[3], const int bc[6], const double *Sin, const
     return m;
 }
 
-// kernel form 'c': the wall cells of a box with bodies (wall_cell_update, the per-thread body of
+// kernel form 'b': the wall cells of a box with bodies (wall_cell_update, the per-thread body of
 // uniform_wall_cells_kernel) into the compact buffer [field][n_list]; returns the largest interface eigenvalue
 
 double emu_wall_cells(int stage, int order, const int dims[3], const int bc[6], double area, double volume, const int clamp[6],

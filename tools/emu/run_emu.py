@@ -117,7 +117,7 @@ class Box:
             vol[:, :, XOFF - 1] = vol[:, :, XOFF]; vol[:, :, nx + XOFF] = vol[:, :, nx + XOFF - 1]
             self.solid = np.zeros(self.fs, np.uint8)
             self.solid[:px * py * pz] = vol.reshape(-1)
-            # kernel forms 'b' and 'c': fluid cells with a wall interface get flag 2 and are listed by padded offset
+            # kernel form 'b': fluid cells with a wall interface get flag 2 and are listed by padded offset
             # (what uniform_try_create builds)
             step = (1, px, px * py)
             walls = []
@@ -216,9 +216,9 @@ class Box:
         est = np.zeros(ntiles, np.float32)
         zero3 = ia([0, 0, 0])
         dirichlet = np.zeros(5)
-        body_form = form in ("b", "c")
+        body_form = form == "b"
         if (self.solid is not None) != body_form:
-            raise RuntimeError("kernel forms 'b' and 'c' are the ones for a box with bodies, and only those")
+            raise RuntimeError("kernel form 'b' is the one for a box with bodies, and only that one")
         flags = self.flag_c if body_form else self.solid
         self.lib.emu_set_solid(flags.ctypes.data if flags is not None else None)
         e_wall, compact = 0.0, None
@@ -299,7 +299,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
         want = np.zeros(est.shape[0])
         if box.solid is not None:
             lam = np.where(m["solved"] != 0, lam, 0.0)   # solid cells are never written: no estimate
-            if form in ("b", "c"):                       # ... nor are the wall cells, by the stage kernel itself
+            if form == "b":                              # ... nor are the wall cells, by the stage kernel itself
                 lam = np.where(box.flag_c[box.off] == 0, lam, 0.0)
         np.maximum.at(want, tile, lam)
         if not np.allclose(est, want, rtol=2e-5, atol=0):
@@ -312,7 +312,7 @@ def check_case(lib, oracle, name, m, order, form, nw, lz, steps, chaos, seed):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--forms", default="r,t,h,c,b")
+    ap.add_argument("--forms", default="r,t,h,b")
     ap.add_argument("--nw", default="8,12,16")
     ap.add_argument("--chaos", type=int, default=0, help="max random delay (us) around mbarrier operations")
     ap.add_argument("--repeat", type=int, default=1)
@@ -331,12 +331,12 @@ def main():
         cases.append(("box 5x23x7 lexi reflecting", lexicographic_box_mesh(5, 23, 7, 0.5, 1), 1, 7))
         cases.append(("box 31x7x2 lexi free-flow", lexicographic_box_mesh(31, 7, 2, 0.5, 0), 1, 1))
         cases.append(("box 33x8x5 lexi reflecting", lexicographic_box_mesh(33, 8, 5, 0.5, 1), 1, 2))
-    # boxes with bodies (kernel forms 'b' and 'c' only): a box body off the Morton cube's centre, two bodies touching
+    # boxes with bodies (kernel form 'b' only): a box body off the Morton cube's centre, two bodies touching
     # the border, a one-cell body
     body_cases = []
-    body_forms = [f for f in forms if f in ("b", "c")]
+    body_forms = [f for f in forms if f == "b"]
     if body_forms:
-        forms = [f for f in forms if f not in ("b", "c")]
+        forms = [f for f in forms if f != "b"]
         body_cases.append(("radsod 16^3 + box body", oracle.problem_mesh("radsod", 3, 16, boxes=[[2.1, 3.2, 1.3, 4.9, 5.4, 3.6]]), 0, 6))
         if not args.quick:
             body_cases.append(("sod3d_x 16^3 + 2 bodies at the border", oracle.problem_mesh(

@@ -61,8 +61,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--problem", default="vortex_xy")
-    ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain (the fused path then runs kernel form 'b'; "
-                    "MMF_UNIFORM_BODIES=2: the rotate form 'c')")
+    ap.add_argument("--bodies", action="store_true", help="two body boxes in the domain (the fused path then runs kernel form 'b')")
     ap.add_argument("--no-generic", action="store_true", help="time the fused path only")
     ap.add_argument("--generic-only", action="store_true", help="time the generic path only")
     ap.add_argument("--dim", type=int, default=3, help="2: the 2-D vortex on size^2 cells (generic path only: the fused path is 3-D)")
@@ -78,7 +77,7 @@ def main():
         return other_meshes(args)
     m = box_mesh(n, n, n, length / n, 0, origin=origin)
     if args.bodies:
-        os.environ.setdefault("MMF_UNIFORM_BODIES", "1")   # 1 = kernel form 'b' (the default), 2 = the rotate form, 'c'
+        os.environ.setdefault("MMF_UNIFORM_BODIES", "1")
         lo = lambda f: [origin[e] + f[e] * length for e in range(3)]
         m = with_bodies(m, [lo((0.30, 0.35, 0.25)) + lo((0.45, 0.60, 0.55)), lo((0.70, 0.10, 0.60)) + lo((0.85, 0.30, 0.95))])
     U = vortex_state(m)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# a box with bodies on the fused path: parity of kernel forms 'b' (default) and 'c', then their step times next to the
+# a box with bodies on the fused path: parity of kernel form 'b', then its step times next to the
 # same box without bodies and to the generic path (one GPU)
 set -u
 mkdir -p gpurun_out
@@ -11,7 +11,6 @@ O=gpurun_out/${TAG}_bodies.jsonl
 for n in 192 256; do
   timeout 300 python tools/generic_bench.py --size $n --steps 20 --no-generic >> $O 2>gpurun_out/${TAG}_bodies.err
   timeout 300 python tools/generic_bench.py --size $n --steps 20 --bodies --no-generic >> $O 2>>gpurun_out/${TAG}_bodies.err
-  MMF_UNIFORM_BODIES=2 timeout 300 python tools/generic_bench.py --size $n --steps 20 --bodies --no-generic >> $O 2>>gpurun_out/${TAG}_bodies.err
 done
 timeout 600 python tools/generic_bench.py --size 192 --steps 10 --bodies >> $O 2>>gpurun_out/${TAG}_bodies.err
 cat $O; tail -3 gpurun_out/${TAG}_bodies.err

@@ -112,8 +112,7 @@ def main():
                 # the rotate form (per-thread global loads): what runs when an x side is a partition side
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb0": "stage2_v5r_12warps",
                 "uniform_stage_kernel_v5rILi2ELi0ELi12ELb1": "stage2_v5r_12warps_xghost",
-                # ... and the rotate form for it (MMF_UNIFORM_BODIES=2), the pass over the wall cells
-                "uniform_stage_kernel_v5rbILi2ELi0ELi12ELb1": "stage2_v5rb_bodies_12warps",
+                # ... and the pass over the wall cells around it
                 "uniform_wall_cells_kernelILi2ELi0": "stage2_wall_cells",
                 "uniform_eig_body_kernel": "uniform_eig_body",
                 "uniform_eig_kernel": "uniform_eig", "uniform_ghost_kernel": "uniform_ghost",
