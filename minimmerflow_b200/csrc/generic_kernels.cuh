@@ -16,6 +16,10 @@ namespace mmf {
 #ifndef MMF_GEN_MINBLOCKS
 #define MMF_GEN_MINBLOCKS 5
 #endif
+// ... and for a 2-D mesh (four entries per cell instead of six and more): 6 blocks, 85 registers, the faster shape there
+#ifndef MMF_GEN_MINBLOCKS_2D
+#define MMF_GEN_MINBLOCKS_2D 6
+#endif
 
 // ---- host AoS (raw order, [c*5+k]) <-> device SoA ([k*stride+c]) -------------------------------
 
@@ -328,8 +332,8 @@ __global__ void __launch_bounds__(256) generic_rk_kernel(int64_t n_cells, int64_
 //            because cellRHS of the reference holds the stage-3 residual when a step ends (it is written
 //            out with the solution, src/main.cpp:284-298)
 // A step switched off on the device (ctl->active == 0) updates nothing, like generic_rk_kernel.
-template <int STAGE>
-__global__ void __launch_bounds__(128, MMF_GEN_MINBLOCKS) generic_stage_kernel(GenericMesh m, const double *__restrict__ Sin,
+template <int STAGE, int MINBLOCKS = MMF_GEN_MINBLOCKS>
+__global__ void __launch_bounds__(128, MINBLOCKS) generic_stage_kernel(GenericMesh m, const double *__restrict__ Sin,
                                                             const double *Un, double *Out, double *__restrict__ RHS,
                                                             const StepControl *__restrict__ ctl,
                                                             double *__restrict__ max_eig)
@@ -361,7 +365,8 @@ __global__ void __launch_bounds__(128, MMF_GEN_MINBLOCKS) generic_stage_kernel(G
 
 // The stage-1 residual of the fused sequence: generic_rhs_kernel's result from generic_cell_residual (the
 // gathering cell derived once).  Stage 1 itself stays two kernels, its dt comes out of this one's maximum.
-__global__ void __launch_bounds__(128, MMF_GEN_MINBLOCKS) generic_rhs_derived_kernel(GenericMesh m, const double *__restrict__ S,
+template <int MINBLOCKS = MMF_GEN_MINBLOCKS>
+__global__ void __launch_bounds__(128, MINBLOCKS) generic_rhs_derived_kernel(GenericMesh m, const double *__restrict__ S,
                                                                   double *__restrict__ RHS, double *__restrict__ max_eig)
 {
     const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

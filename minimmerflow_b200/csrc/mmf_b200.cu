@@ -347,8 +347,11 @@ static int rhs_enqueue(mmf_ctx *ctx, int field, int slot, bool derived = false)
     if (ctx->path == MMF_PATH_UNIFORM) return uniform_rhs(ctx, field, d_max);
     {
         ScopedLaunchTimer timer(ctx, 0);
-        if (derived) {
-            generic_rhs_derived_kernel<<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
+        if (derived && ctx->dim == 2) { // (the register budget that is fastest for four entries per cell)
+            generic_rhs_derived_kernel<MMF_GEN_MINBLOCKS_2D><<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
+                ctx->gm, ctx->fields[field], ctx->fields[MMF_FIELD_RHS], d_max);
+        } else if (derived) {
+            generic_rhs_derived_kernel<><<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
                 ctx->gm, ctx->fields[field], ctx->fields[MMF_FIELD_RHS], d_max);
         } else {
             generic_rhs_kernel<<<grid_for(ctx->n_cells, 128), 128, 0, ctx->stream>>>(
@@ -383,8 +386,13 @@ static int generic_stage_enqueue(mmf_ctx *ctx, int stage)
     const unsigned grid = grid_for(ctx->n_cells, 128);
     {
         ScopedLaunchTimer timer(ctx, stage);
-        if (stage == 2) generic_stage_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, ctx->w_alt, R, ctx->d_ctl, d_max);
-        else            generic_stage_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, U, R, ctx->d_ctl, d_max);
+        if (ctx->dim == 2) {
+            if (stage == 2) generic_stage_kernel<2, MMF_GEN_MINBLOCKS_2D><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, ctx->w_alt, R, ctx->d_ctl, d_max);
+            else            generic_stage_kernel<3, MMF_GEN_MINBLOCKS_2D><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, U, R, ctx->d_ctl, d_max);
+        } else {
+            if (stage == 2) generic_stage_kernel<2><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, ctx->w_alt, R, ctx->d_ctl, d_max);
+            else            generic_stage_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->gm, W, U, U, R, ctx->d_ctl, d_max);
+        }
     }
     MMF_LAUNCH_CHECK(ctx);
     if (stage == 2) std::swap(ctx->fields[MMF_FIELD_W], ctx->w_alt); // field W is what stage 2 wrote

@@ -477,7 +477,7 @@ int emu_generic_run(const mmf_mesh_desc *d, int fused, double *U, double *W, dou
     auto rhs = [&](const double *S, int slot) {
         ctl.max_eig[slot] = 0.0;
         double *mx = &ctl.max_eig[slot];
-        if (fused) run([=] { generic_rhs_derived_kernel(m, S, RHS, mx); });
+        if (fused) run([=] { generic_rhs_derived_kernel<>(m, S, RHS, mx); });
         else       run([=] { generic_rhs_kernel(m, S, RHS, mx); });
     };
     StepControl *c = &ctl;
