@@ -35,6 +35,31 @@ def test_struct_sizes_match_header_layout(mmf):
     assert C.sizeof(_cabi.UniformDesc) % 8 == 0
 
 
+def test_uniform_descriptor_sizes_accepted(mmf):
+    """mmf_uniform_desc grew by the optional `area` / `volume` fields: a caller built against the shorter struct
+    (struct_size = offset of `area`) is still served, any other size is an ABI mismatch -- decided before a device is
+    looked for, so the check runs without a GPU (where the accepted sizes then fail with MMF_ERR_NO_DEVICE)."""
+    from minimmerflow_b200 import _cabi
+    lib = mmf.load_library()
+    full, legacy = C.sizeof(_cabi.UniformDesc), _cabi.UniformDesc.area.offset
+    assert legacy == full - 16
+    for size, ok in ((full, True), (legacy, True), (full - 8, False), (full + 8, False), (0, False)):
+        d = _cabi.UniformDesc()
+        d.struct_size = size
+        for e in range(3):
+            d.box_dims[e] = d.global_dims[e] = 4
+        d.h = 1.0
+        h = C.c_void_p()
+        rc = lib.mmf_create_uniform(C.byref(d), 0, C.byref(h))
+        if h.value:
+            lib.mmf_destroy(h)
+        if ok:
+            assert rc in (0, 4), (size, rc)        # MMF_OK on a B200, MMF_ERR_NO_DEVICE without one
+        else:
+            assert rc == 1, (size, rc)             # MMF_ERR_INVALID
+            assert b"ABI mismatch" in lib.mmf_last_error(None)
+
+
 def test_no_gpu_means_loud_failure(mmf, oracle):
     if mmf.device_count() > 0:
         pytest.skip("a B200 is present")
